@@ -1,0 +1,1310 @@
+// solver.cu — host side of libbendy2d_b200.so: scene store, link planning, launch sequencing,
+// CUDA-graph capture of the substep, and the C ABI declared in include/bendy2d_b200.h.
+//
+// Mirrors the reference's `Solver` (src/solver.rs:20-116).  The substep order is the reference's
+// (solver.rs:109-115): gravity -> links -> dynamic collisions -> bounds -> integrate, with gravity
+// fused into the integrate kernel (acc is zero between substeps: particle.rs:24, solver.rs:110).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/bendy2d_b200.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+using namespace bendy;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // grows (never shrinks); contents are NOT preserved
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        release();
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return e;
+        }
+        cap = want;
+        return cudaSuccess;
+    }
+};
+
+struct PolyHost {
+    uint32_t start = 0, nv = 0;  // into the polygon point arrays
+    uint32_t link_start = 0, nl = 0;
+    bool is_static = false;
+    float2 center = {0.f, 0.f};
+};
+
+struct PendingEvent {
+    int cls;
+    cudaEvent_t e0, e1;
+};
+
+}  // namespace
+
+struct bendy_solver {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int sticky = BENDY_OK;
+
+    // ---------------- host scene, USER order (solver.rs:24-28)
+    std::vector<float2> p_pos, p_prev;  // free particles (acc is always 0 at add: solver.rs:52-54)
+    std::vector<float> p_k;             // ext inverse-mass scale, empty = all 1
+    std::vector<float2> c_pos, c_prev, c_acc;
+    std::vector<float> c_rad, c_k;
+    std::vector<uint32_t> pl_ab;  // particle links
+    std::vector<float> pl_len;
+    std::vector<GlobalLink> cl;   // circle links
+    std::vector<PolyHost> polys;
+    std::vector<float2> g_pos, g_prev, g_acc;  // polygon points, polygon-major
+    std::vector<uint32_t> gl_ab;               // polygon-local link indices
+    std::vector<float> gl_len;
+    bool any_acc = false;  // some circle / polygon point was added with acc != 0
+
+    uint16_t sub_steps = 1;
+    float particle_radius = 0.f;
+    float grid_cell = 0.f;
+    bool polygon_contact = false;
+    PlanParams plan_params;
+
+    // ---------------- state location
+    bool host_valid = true;     // host vectors hold the current pos/prev
+    bool device_valid = false;  // device buffers hold the current pos/prev
+    bool topo_dirty = true;     // plan / device tables must be rebuilt
+
+    // ---------------- plan + device tables
+    LinkPlan plan_p, plan_g;
+    uint32_t nP = 0, nC = 0, nG = 0, N = 0, Npad = 0;
+    DevBuf<float2> d_pos, d_prev, d_accel, d_stage;
+    DevBuf<float> d_k, d_crad;
+    DevBuf<uint8_t> d_gstatic;
+    DevBuf<uint32_t> d_rank;  // user particle -> internal
+    DevBuf<uint32_t> d_part_start, d_part_cs, d_gpart_start, d_gpart_cs;
+    DevBuf<LocalLink> d_local, d_glocal;
+    DevBuf<GlobalLink> d_global, d_gglobal, d_clinks;
+    bool accel_pending = false;
+    bool has_k = false;
+    // grid
+    DevBuf<uint32_t> d_cell_of, d_cell_count, d_cell_start, d_tile_sum, d_slot_id, d_sorted_id;
+    DevBuf<float2> d_sorted_pos;
+    DevBuf<uint32_t> d_circ_tiles;
+    DevBuf<unsigned long long> d_circ_acc;
+    uint32_t n_cells = 0;
+    // polygons
+    DevBuf<uint32_t> d_poly_start, d_poly_tiles;
+    DevBuf<uint8_t> d_poly_static;
+    DevBuf<float2> d_poly_center;
+    DevBuf<float4> d_poly_box;
+    float poly_tile = 0.f;
+    uint32_t n_poly_tiles = 0;
+    DevBuf<int> d_flags;
+
+    // ---------------- per-update params
+    DevBuf<StepParams> d_prm;
+    StepParams prm{};
+    bool prm_valid = false;
+    StepParams *h_prm_ring = nullptr;  // pinned
+    uint32_t prm_ring_pos = 0;
+    static constexpr uint32_t kPrmRing = 64;
+    cudaEvent_t prm_ring_ev[kPrmRing] = {};
+
+    // ---------------- launch machinery
+    bool profiling = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint32_t graph_substeps = 0;
+    uint32_t kernels_per_substep = 0;
+    uint64_t launches = 0;
+    double k_ms[BENDY_K_CLASSES] = {};
+    uint64_t k_launches[BENDY_K_CLASSES] = {};
+    std::vector<PendingEvent> pending;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool capturing = false;
+    uint32_t count_in_capture = 0;
+
+    ~bendy_solver();
+};
+
+namespace {
+
+// inside Ops member functions
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) return this->fail_cuda(_e, #call, __LINE__);                           \
+    } while (0)
+
+struct Ops {  // helper with access to the solver; keeps bendy_solver a plain struct
+    bendy_solver *s;
+    int fail(int code, const std::string &msg) {
+        s->err = msg;
+        g_last_error = msg;
+        return code;
+    }
+    int fail_cuda(cudaError_t e, const char *what, int line) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %s (%s) at solver.cu:%d: %s", cudaGetErrorName(e),
+                 cudaGetErrorString(e), line, what);
+        s->sticky = BENDY_ERR_CUDA;
+        return fail(BENDY_ERR_CUDA, buf);
+    }
+
+    int bind() {
+        cudaError_t e = cudaSetDevice(s->device);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice", __LINE__);
+        return BENDY_OK;
+    }
+
+    // ---- state movement -------------------------------------------------------------------
+    int pull();         // device -> host vectors (user order)
+    int rebuild();      // plan + upload everything
+    int ensure_ready(); // before update / device reads
+    int configure(float dt, float gx, float gy, float bx, float by, float bw, float bh);
+    int grid_for(float bx, float by, float bw, float bh, StepParams *p, uint32_t *ncells);
+    int enqueue_substeps(uint32_t count);
+    int launch_substep();
+    int build_graph(uint32_t substeps);
+    void drop_graph();
+    int flush_events();
+    int check_flags();
+
+    template <typename F>
+    int launch(int cls, F &&f);
+};
+
+void Ops::drop_graph() {
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    s->graph_exec = nullptr;
+    s->graph_substeps = 0;
+}
+
+template <typename F>
+int Ops::launch(int cls, F &&f) {
+    if (s->capturing) {
+        f();
+        s->count_in_capture++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(e, "kernel launch (capture)", __LINE__);
+        return BENDY_OK;
+    }
+    if (s->profiling) {
+        cudaEvent_t e0, e1;
+        for (cudaEvent_t *pe : {&e0, &e1}) {
+            if (!s->event_pool.empty()) {
+                *pe = s->event_pool.back();
+                s->event_pool.pop_back();
+            } else {
+                CK(cudaEventCreate(pe));
+            }
+        }
+        CK(cudaEventRecord(e0, s->stream));
+        f();
+        CK(cudaEventRecord(e1, s->stream));
+        s->pending.push_back(PendingEvent{cls, e0, e1});
+    } else {
+        f();
+    }
+    s->launches++;
+    s->k_launches[cls]++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "kernel launch", __LINE__);
+    if (s->pending.size() >= 8192) return flush_events();
+    return BENDY_OK;
+}
+
+int Ops::flush_events() {
+    if (s->pending.empty()) return BENDY_OK;
+    CK(cudaStreamSynchronize(s->stream));
+    for (PendingEvent &pe : s->pending) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, pe.e0, pe.e1));
+        s->k_ms[pe.cls] += ms;
+        s->event_pool.push_back(pe.e0);
+        s->event_pool.push_back(pe.e1);
+    }
+    s->pending.clear();
+    return BENDY_OK;
+}
+
+int Ops::check_flags() {
+    if (!s->d_flags.p) return BENDY_OK;
+    int f = 0;
+    CK(cudaMemcpyAsync(&f, s->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (f) {
+        CK(cudaMemsetAsync(s->d_flags.p, 0, sizeof(int), s->stream));
+        if (f & (FLAG_POLY_TILE_OVERFLOW | FLAG_POLY_SPAN_OVERFLOW))
+            return fail(BENDY_ERR_UNSUPPORTED,
+                        "polygon broadphase overflow: more than 7 polygons share one tile or a polygon spans "
+                        "more than 64 tiles; particle-polygon contacts were dropped for the overflowing tiles");
+    }
+    return BENDY_OK;
+}
+
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// device -> host (USER order).  Used before the scene is edited after a run.
+int Ops::pull() {
+    if (s->host_valid) return BENDY_OK;
+    if (!s->device_valid) return fail(BENDY_ERR_ARG, "internal: no valid state");
+    if (int rc = bind()) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+    std::vector<float2> tmp(s->N);
+    for (int which = 0; which < 2; which++) {
+        const float2 *src = which == 0 ? s->d_pos.p : s->d_prev.p;
+        if (s->N) CK(cudaMemcpy(tmp.data(), src, (size_t)s->N * sizeof(float2), cudaMemcpyDeviceToHost));
+        std::vector<float2> &P = which == 0 ? s->p_pos : s->p_prev;
+        std::vector<float2> &Cc = which == 0 ? s->c_pos : s->c_prev;
+        std::vector<float2> &G = which == 0 ? s->g_pos : s->g_prev;
+        for (uint32_t i = 0; i < s->nP; i++) P[i] = tmp[s->plan_p.rank[i]];
+        for (uint32_t i = 0; i < s->nC; i++) Cc[i] = tmp[s->nP + i];
+        for (uint32_t i = 0; i < s->nG; i++) G[i] = tmp[s->nP + s->nC + i];
+    }
+    if (s->accel_pending && s->d_accel.p) {
+        CK(cudaMemcpy(tmp.data(), s->d_accel.p, (size_t)s->N * sizeof(float2), cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < s->nC; i++) s->c_acc[i] = tmp[s->nP + i];
+        for (uint32_t i = 0; i < s->nG; i++) s->g_acc[i] = tmp[s->nP + s->nC + i];
+    } else {
+        // acc was consumed and cleared by the first integrate (particle.rs:24)
+        std::fill(s->c_acc.begin(), s->c_acc.end(), make_float2(0.f, 0.f));
+        for (size_t k = 0; k < s->polys.size(); k++)
+            if (!s->polys[k].is_static)
+                std::fill(s->g_acc.begin() + s->polys[k].start, s->g_acc.begin() + s->polys[k].start + s->polys[k].nv,
+                          make_float2(0.f, 0.f));
+        s->any_acc = false;
+        for (const float2 &a : s->g_acc)
+            if (a.x != 0.f || a.y != 0.f) s->any_acc = true;
+    }
+    // polygon centres: Polygon.center after update() is the mean of the pre-integrate positions
+    // (polygon.rs:130 -> calc_center on what is now prev_pos); static polygons keep the value
+    // computed by solve_links (polygon.rs:219), which the device stores in d_poly_center.
+    if (!s->polys.empty()) {
+        std::vector<float2> cen(s->polys.size());
+        CK(cudaMemcpy(cen.data(), s->d_poly_center.p, cen.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < s->polys.size(); k++) {
+            PolyHost &P = s->polys[k];
+            if (P.is_static) {
+                P.center = cen[k];
+            } else {
+                float cx = 0.f, cy = 0.f;
+                for (uint32_t v = 0; v < P.nv; v++) {
+                    cx = cx + s->g_prev[P.start + v].x;
+                    cy = cy + s->g_prev[P.start + v].y;
+                }
+                P.center = make_float2(cx / (float)P.nv, cy / (float)P.nv);
+            }
+        }
+    }
+    s->host_valid = true;
+    return BENDY_OK;
+}
+
+template <typename T>
+static cudaError_t upload(DevBuf<T> &d, const std::vector<T> &h, cudaStream_t st) {
+    cudaError_t e = d.ensure(std::max<size_t>(h.size(), 1));
+    if (e != cudaSuccess) return e;
+    if (h.empty()) return cudaSuccess;
+    return cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+int Ops::rebuild() {
+    if (int rc = bind()) return rc;
+    if (int rc = pull()) return rc;
+    drop_graph();
+    s->nP = (uint32_t)s->p_pos.size();
+    s->nC = (uint32_t)s->c_pos.size();
+    s->nG = (uint32_t)s->g_pos.size();
+    s->N = s->nP + s->nC + s->nG;
+    s->Npad = (s->N + 1u) & ~1u;
+    std::string perr;
+    if (!plan_links(s->nP, s->pl_ab.data(), s->pl_len.data(), s->pl_len.size(), s->plan_params, false, &s->plan_p,
+                    &perr))
+        return fail(BENDY_ERR_UNSUPPORTED, perr);
+    // polygon-internal links (polygon.rs:218-223) use polygon-local indices: rebase to the polygon
+    // point array; the order of polygon points is part of the shape, so keep_order = true
+    {
+        std::vector<uint32_t> ab(s->gl_ab.size());
+        for (const PolyHost &P : s->polys)
+            for (uint32_t k = 0; k < P.nl; k++) {
+                ab[2 * (P.link_start + k)] = s->gl_ab[2 * (P.link_start + k)] + P.start;
+                ab[2 * (P.link_start + k) + 1] = s->gl_ab[2 * (P.link_start + k) + 1] + P.start;
+            }
+        if (!plan_links(s->nG, ab.data(), s->gl_len.data(), s->gl_len.size(), s->plan_params, true, &s->plan_g,
+                        &perr))
+            return fail(BENDY_ERR_UNSUPPORTED, perr);
+    }
+    // ---- state upload (internal order)
+    std::vector<float2> pos(s->Npad), prev(s->Npad);
+    for (uint32_t i = 0; i < s->nP; i++) {
+        pos[s->plan_p.rank[i]] = s->p_pos[i];
+        prev[s->plan_p.rank[i]] = s->p_prev[i];
+    }
+    std::copy(s->c_pos.begin(), s->c_pos.end(), pos.begin() + s->nP);
+    std::copy(s->c_prev.begin(), s->c_prev.end(), prev.begin() + s->nP);
+    std::copy(s->g_pos.begin(), s->g_pos.end(), pos.begin() + s->nP + s->nC);
+    std::copy(s->g_prev.begin(), s->g_prev.end(), prev.begin() + s->nP + s->nC);
+    for (uint32_t i = s->N; i < s->Npad; i++) pos[i] = prev[i] = make_float2(0.f, 0.f);
+    CK(upload(s->d_pos, pos, s->stream));
+    CK(upload(s->d_prev, prev, s->stream));
+    CK(s->d_stage.ensure(std::max<size_t>(s->Npad, 1)));
+    s->accel_pending = false;
+    if (s->any_acc) {
+        std::vector<float2> acc(s->Npad, make_float2(0.f, 0.f));
+        std::copy(s->c_acc.begin(), s->c_acc.end(), acc.begin() + s->nP);
+        std::copy(s->g_acc.begin(), s->g_acc.end(), acc.begin() + s->nP + s->nC);
+        CK(upload(s->d_accel, acc, s->stream));
+        s->accel_pending = true;
+    }
+    s->has_k = !s->p_k.empty() || !s->c_k.empty();
+    if (s->has_k) {
+        std::vector<float> k(s->Npad, 1.0f);
+        if (!s->p_k.empty())
+            for (uint32_t i = 0; i < s->nP; i++) k[s->plan_p.rank[i]] = s->p_k[i];
+        if (!s->c_k.empty()) std::copy(s->c_k.begin(), s->c_k.end(), k.begin() + s->nP);
+        CK(upload(s->d_k, k, s->stream));
+    }
+    CK(upload(s->d_crad, s->c_rad, s->stream));
+    CK(upload(s->d_rank, s->plan_p.rank, s->stream));
+    // ---- link tables
+    CK(upload(s->d_part_start, s->plan_p.part_start, s->stream));
+    CK(upload(s->d_part_cs, s->plan_p.part_colour_start, s->stream));
+    CK(upload(s->d_local, s->plan_p.local_links, s->stream));
+    CK(upload(s->d_global, s->plan_p.global_links, s->stream));
+    CK(upload(s->d_gpart_start, s->plan_g.part_start, s->stream));
+    CK(upload(s->d_gpart_cs, s->plan_g.part_colour_start, s->stream));
+    CK(upload(s->d_glocal, s->plan_g.local_links, s->stream));
+    CK(upload(s->d_gglobal, s->plan_g.global_links, s->stream));
+    CK(upload(s->d_clinks, s->cl, s->stream));
+    // ---- polygons
+    {
+        std::vector<uint32_t> pstart(s->polys.size() + 1, 0);
+        std::vector<uint8_t> pstatic(s->polys.size()), gstatic(s->nG);
+        std::vector<float2> cen(s->polys.size());
+        float ext = 0.f;
+        for (size_t k = 0; k < s->polys.size(); k++) {
+            const PolyHost &P = s->polys[k];
+            pstart[k] = P.start;
+            pstart[k + 1] = P.start + P.nv;
+            pstatic[k] = P.is_static ? 1 : 0;
+            cen[k] = P.center;
+            float x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
+            for (uint32_t v = 0; v < P.nv; v++) {
+                gstatic[P.start + v] = pstatic[k];
+                float2 p = s->g_pos[P.start + v];
+                x0 = std::fmin(x0, p.x), y0 = std::fmin(y0, p.y), x1 = std::fmax(x1, p.x), y1 = std::fmax(y1, p.y);
+            }
+            if (std::isfinite(x1 - x0)) ext = std::fmax(ext, x1 - x0);
+            if (std::isfinite(y1 - y0)) ext = std::fmax(ext, y1 - y0);
+        }
+        s->poly_tile = ext > 0.f ? ext : 1.0f;
+        CK(upload(s->d_poly_start, pstart, s->stream));
+        CK(upload(s->d_poly_static, pstatic, s->stream));
+        CK(upload(s->d_gstatic, gstatic, s->stream));
+        CK(upload(s->d_poly_center, cen, s->stream));
+        CK(s->d_poly_box.ensure(std::max<size_t>(s->polys.size(), 1)));
+    }
+    if (!s->d_flags.p) {
+        CK(s->d_flags.ensure(1));
+        CK(cudaMemsetAsync(s->d_flags.p, 0, sizeof(int), s->stream));
+    }
+    CK(s->d_prm.ensure(1));
+    if (!s->h_prm_ring) {
+        CK(cudaHostAlloc(&s->h_prm_ring, sizeof(StepParams) * bendy_solver::kPrmRing, cudaHostAllocDefault));
+        for (uint32_t i = 0; i < bendy_solver::kPrmRing; i++)
+            CK(cudaEventCreateWithFlags(&s->prm_ring_ev[i], cudaEventDisableTiming));
+    }
+    // grid buffers that depend only on the particle count
+    if (s->nP) {
+        CK(s->d_cell_of.ensure(s->nP));
+        CK(s->d_slot_id.ensure(s->nP));
+        CK(s->d_sorted_id.ensure(s->nP));
+        CK(s->d_sorted_pos.ensure(s->nP));
+    }
+    if (s->nC) {
+        CK(s->d_circ_acc.ensure(2 * (size_t)s->nC));
+        CK(cudaMemsetAsync(s->d_circ_acc.p, 0, 2 * (size_t)s->nC * sizeof(unsigned long long), s->stream));
+    }
+    CK(cudaStreamSynchronize(s->stream));  // host staging vectors die here
+    s->prm_valid = false;
+    s->n_cells = 0;
+    s->topo_dirty = false;
+    s->device_valid = true;
+    return BENDY_OK;
+}
+
+int Ops::ensure_ready() {
+    if (s->sticky != BENDY_OK) return fail(s->sticky, s->err);
+    if (s->topo_dirty || !s->device_valid) return rebuild();
+    return bind();
+}
+
+// broadphase grid for these bounds: origin = bounds.pos, h >= 2*r_p, cell count bounded
+int Ops::grid_for(float bx, float by, float bw, float bh, StepParams *p, uint32_t *ncells) {
+    float h = s->grid_cell > 0.f ? s->grid_cell : 2.0f * s->particle_radius;
+    if (h < 2.0f * s->particle_radius) h = 2.0f * s->particle_radius;
+    if (!(h > 0.f)) h = 1.0f;
+    const double max_cells = 67108864.0;  // 2^26
+    double wx = std::isfinite(bw) && bw > 0.f ? bw : 1.0, wy = std::isfinite(bh) && bh > 0.f ? bh : 1.0;
+    while (std::ceil(wx / h) * std::ceil(wy / h) > max_cells) h *= 1.25f;
+    int nx = (int)std::ceil(wx / h), ny = (int)std::ceil(wy / h);
+    nx = std::max(nx, 1), ny = std::max(ny, 1);
+    p->gox = bx, p->goy = by, p->h = h, p->inv_h = 1.0f / h;
+    p->nx = nx, p->ny = ny;
+    p->tnx = (nx + (1 << BENDY_TILE_SHIFT) - 1) >> BENDY_TILE_SHIFT;
+    p->tny = (ny + (1 << BENDY_TILE_SHIFT) - 1) >> BENDY_TILE_SHIFT;
+    *ncells = (uint32_t)nx * (uint32_t)ny;
+    return BENDY_OK;
+}
+
+int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, float bh) {
+    StepParams p = s->prm;
+    p.gx = gx, p.gy = gy, p.dt = dt;
+    p.gdt2x = (gx * dt) * dt;  // particle.rs:23: acc * dt * dt, left-associative
+    p.gdt2y = (gy * dt) * dt;
+    p.lo_x = bx, p.lo_y = by;
+    p.hi_x = bx + bw;  // particle.rs:32
+    p.hi_y = by + bh;  // particle.rs:41
+    p.rp = s->particle_radius;
+    uint32_t ncells = 0;
+    const bool discs = s->particle_radius > 0.f && s->nP > 0;
+    if (discs) {
+        grid_for(bx, by, bw, bh, &p, &ncells);
+    } else {
+        p.nx = p.ny = p.tnx = p.tny = 1, p.gox = bx, p.goy = by, p.h = 1.f, p.inv_h = 1.f;
+    }
+    const bool contact = s->polygon_contact && !s->polys.empty() && s->nP > 0;
+    uint32_t ptiles = 0;
+    if (contact) {
+        float t = s->poly_tile;
+        double wx = std::isfinite(bw) && bw > 0.f ? bw : 1.0, wy = std::isfinite(bh) && bh > 0.f ? bh : 1.0;
+        while (std::ceil(wx / t) * std::ceil(wy / t) > 4194304.0) t *= 1.25f;
+        p.pox = bx, p.poy = by, p.psize = t, p.pinv = 1.0f / t;
+        p.pnx = std::max(1, (int)std::ceil(wx / t)), p.pny = std::max(1, (int)std::ceil(wy / t));
+        ptiles = (uint32_t)p.pnx * (uint32_t)p.pny;
+    } else {
+        p.pox = bx, p.poy = by, p.psize = 1.f, p.pinv = 1.f, p.pnx = p.pny = 1;
+    }
+    bool same = s->prm_valid && std::memcmp(&p, &s->prm, sizeof p) == 0;
+    if (same) return BENDY_OK;
+    // grid shape changes invalidate captured launch dimensions
+    bool shape = !s->prm_valid || p.nx != s->prm.nx || p.ny != s->prm.ny || p.pnx != s->prm.pnx ||
+                 p.pny != s->prm.pny;
+    if (shape) {
+        drop_graph();
+        if (discs) {
+            s->n_cells = ncells;
+            CK(s->d_cell_count.ensure(ncells));
+            CK(cudaMemsetAsync(s->d_cell_count.p, 0, (size_t)ncells * sizeof(uint32_t), s->stream));
+            CK(s->d_cell_start.ensure(ncells));
+            CK(s->d_tile_sum.ensure(cdiv(ncells, SCAN_TILE) + 1));
+            if (s->nC) CK(s->d_circ_tiles.ensure((size_t)p.tnx * p.tny * (BENDY_CIRC_CAP + 1)));
+        }
+        if (contact) {
+            s->n_poly_tiles = ptiles;
+            CK(s->d_poly_tiles.ensure((size_t)ptiles * (BENDY_POLY_CAP + 1)));
+        }
+    }
+    s->prm = p;
+    s->prm_valid = true;
+    // stage through a pinned ring so the async copy never reads a host value that changed later
+    uint32_t slot = s->prm_ring_pos++ % bendy_solver::kPrmRing;
+    if (s->prm_ring_pos > bendy_solver::kPrmRing) CK(cudaEventSynchronize(s->prm_ring_ev[slot]));
+    s->h_prm_ring[slot] = p;
+    CK(cudaMemcpyAsync(s->d_prm.p, &s->h_prm_ring[slot], sizeof p, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaEventRecord(s->prm_ring_ev[slot], s->stream));
+    return BENDY_OK;
+}
+
+#define LAUNCH(cls, ...)                                         \
+    do {                                                         \
+        int _rc = launch((cls), [&]() { __VA_ARGS__; });         \
+        if (_rc) return _rc;                                     \
+    } while (0)
+
+// one substep, reference order (solver.rs:109-115)
+int Ops::launch_substep() {
+    cudaStream_t st = s->stream;
+    const StepParams *prm = s->d_prm.p;
+    const bool K = s->has_k;
+    float2 *pos = s->d_pos.p;
+    const uint32_t nPoly = (uint32_t)s->polys.size();
+    const bool contact = s->polygon_contact && nPoly && s->nP;
+    const bool discs = s->particle_radius > 0.f && s->nP;
+
+    // -- polygon centres (Polygon::solve_links calls calc_center first: polygon.rs:219) + bins
+    if (nPoly) {
+        PolyArgs pa{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_static.p, nPoly, s->d_poly_center.p,
+                    s->d_poly_box.p,     s->d_poly_tiles.p, s->d_flags.p};
+        if (contact) {
+            // zero the tile counters (count word of every tile)
+            LAUNCH(BENDY_K_POLY_PREP, cudaMemsetAsync(s->d_poly_tiles.p, 0,
+                                                      (size_t)s->n_poly_tiles * (BENDY_POLY_CAP + 1) * sizeof(uint32_t), st));
+        }
+        LAUNCH(BENDY_K_POLY_PREP, k4_poly_prep<<<cdiv(nPoly, 128), 128, 0, st>>>(pa, prm, contact ? 1 : 0));
+    }
+    // -- apply_links (solver.rs:143-153): particle links, circle links, polygon links
+    auto run_plan = [&](const LinkPlan &P, uint32_t base, const uint32_t *d_ps, const uint32_t *d_cs,
+                        const LocalLink *d_l, const GlobalLink *d_g) -> int {
+        if (P.n_parts() && !P.local_links.empty()) {
+            uint32_t maxp = 0;
+            for (uint32_t p = 0; p < P.n_parts(); p++) maxp = std::max(maxp, P.part_start[p + 1] - P.part_start[p]);
+            size_t smem = (size_t)maxp * (K ? 12 : 8);
+            if (K)
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true><<<P.n_parts(), 256, smem, st>>>(
+                                                pos, s->d_k.p, base, d_ps, d_cs, d_l, P.n_local_colours));
+            else
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false><<<P.n_parts(), 256, smem, st>>>(
+                                                pos, nullptr, base, d_ps, d_cs, d_l, P.n_local_colours));
+        }
+        for (uint32_t c = 0; c < P.n_global_colours(); c++) {
+            uint32_t l0 = P.gcolour_start[c], l1 = P.gcolour_start[c + 1];
+            if (l0 == l1) continue;
+            if (K)
+                LAUNCH(BENDY_K_LINKS_GLOBAL,
+                       k3_links_global<true><<<cdiv(l1 - l0, 256), 256, 0, st>>>(pos, s->d_k.p, base, d_g, l0, l1));
+            else
+                LAUNCH(BENDY_K_LINKS_GLOBAL,
+                       k3_links_global<false><<<cdiv(l1 - l0, 256), 256, 0, st>>>(pos, nullptr, base, d_g, l0, l1));
+        }
+        return BENDY_OK;
+    };
+    if (int rc = run_plan(s->plan_p, 0, s->d_part_start.p, s->d_part_cs.p, s->d_local.p, s->d_global.p)) return rc;
+    if (!s->cl.empty())
+        LAUNCH(BENDY_K_LINKS_CIRCLE,
+               k3_circle_links<<<1, 32, 0, st>>>(pos + s->nP, s->d_crad.p, s->d_clinks.p, (uint32_t)s->cl.size()));
+    if (int rc = run_plan(s->plan_g, s->nP + s->nC, s->d_gpart_start.p, s->d_gpart_cs.p, s->d_glocal.p,
+                          s->d_gglobal.p))
+        return rc;
+
+    // -- solve_dynamic_collisions (solver.rs:167-188)
+    if (s->nC >= 2) {
+        size_t smem = s->nC <= 4096 ? (size_t)s->nC * 12 : 0;
+        LAUNCH(BENDY_K_CIRCLES, k_circles_exact<<<1, 1024, smem, st>>>(pos + s->nP, s->d_crad.p, s->nC, smem ? 1 : 0));
+    }
+    if (discs) {
+        const uint32_t n_tiles = cdiv(s->n_cells, SCAN_TILE);
+        LAUNCH(BENDY_K_GRID_BUILD,
+               k2_hash_count<<<cdiv(s->nP, 256), 256, 0, st>>>(pos, s->nP, prm, s->d_cell_of.p, s->d_cell_count.p));
+        LAUNCH(BENDY_K_GRID_BUILD,
+               k2_scan_a<<<n_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->n_cells, s->d_tile_sum.p));
+        LAUNCH(BENDY_K_GRID_BUILD, k2_scan_b<<<1, SCAN_THREADS, 0, st>>>(s->d_tile_sum.p, n_tiles));
+        LAUNCH(BENDY_K_GRID_BUILD, k2_scan_c<<<n_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->n_cells,
+                                                                                s->d_tile_sum.p, s->d_cell_start.p));
+        LAUNCH(BENDY_K_GRID_BUILD,
+               k2_scatter<<<cdiv(s->nP, 256), 256, 0, st>>>(s->d_cell_of.p, s->nP, s->d_cell_start.p, s->d_slot_id.p));
+        LAUNCH(BENDY_K_GRID_BUILD,
+               k2_canon<<<cdiv(s->nP, 256), 256, 0, st>>>(s->d_slot_id.p, s->d_cell_of.p, s->d_cell_start.p, s->n_cells,
+                                                          pos, s->d_sorted_id.p, s->d_sorted_pos.p));
+        if (s->nC)
+            LAUNCH(BENDY_K_CIRCLES, k2_circle_bin<<<cdiv((uint32_t)(s->prm.tnx * s->prm.tny), 128), 128, 0, st>>>(
+                                        pos + s->nP, s->d_crad.p, s->nC, prm, s->d_circ_tiles.p));
+        K2Args a{pos,        K ? s->d_k.p : nullptr, s->d_sorted_id.p, s->d_sorted_pos.p,
+                 s->d_cell_start.p, s->n_cells,      s->nP,            s->nC,
+                 s->d_crad.p,       s->nC ? s->d_circ_tiles.p : nullptr, s->d_circ_acc.p};
+        if (K)
+            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow<true><<<cdiv(s->nP, 128), 128, 0, st>>>(a, prm));
+        else
+            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow<false><<<cdiv(s->nP, 128), 128, 0, st>>>(a, prm));
+        if (s->nC)
+            LAUNCH(BENDY_K_CIRCLES, k2_circle_apply<<<cdiv(s->nC, 128), 128, 0, st>>>(pos + s->nP, s->d_circ_acc.p, s->nC));
+    }
+    if (contact) {
+        K4Args a{pos,
+                 K ? s->d_k.p : nullptr,
+                 s->nP,
+                 pos + s->nP + s->nC,
+                 s->d_poly_start.p,
+                 s->d_poly_center.p,
+                 s->d_poly_box.p,
+                 s->d_poly_tiles.p};
+        if (K)
+            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<true><<<cdiv(s->nP, 128), 128, 0, st>>>(a, prm));
+        else
+            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<false><<<cdiv(s->nP, 128), 128, 0, st>>>(a, prm));
+    }
+    // -- solve_boundary_collisions + update_positions (solver.rs:113-114), gravity fused
+    {
+        K1Args a{pos,         s->d_prev.p,       s->accel_pending ? s->d_accel.p : nullptr, K ? s->d_k.p : nullptr,
+                 s->d_crad.p, s->d_gstatic.p, s->nP, s->nC, s->N};
+        uint32_t blocks = cdiv(s->Npad / 2, 256);
+        if (blocks) {
+            if (s->accel_pending) {
+                if (K)
+                    LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, true><<<blocks, 256, 0, st>>>(a, prm));
+                else
+                    LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, false><<<blocks, 256, 0, st>>>(a, prm));
+            } else {
+                if (K)
+                    LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, true><<<blocks, 256, 0, st>>>(a, prm));
+                else
+                    LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, false><<<blocks, 256, 0, st>>>(a, prm));
+            }
+        }
+    }
+    return BENDY_OK;
+}
+
+int Ops::build_graph(uint32_t substeps) {
+    drop_graph();
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    s->capturing = true;
+    s->count_in_capture = 0;
+    int rc = BENDY_OK;
+    for (uint32_t k = 0; k < substeps && rc == BENDY_OK; k++) rc = launch_substep();
+    s->capturing = false;
+    cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture", __LINE__);
+    e = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGraphInstantiate", __LINE__);
+    s->graph_substeps = substeps;
+    s->kernels_per_substep = substeps ? s->count_in_capture / substeps : 0;
+    return BENDY_OK;
+}
+
+// `count` update() calls worth of substeps
+int Ops::enqueue_substeps(uint32_t updates) {
+    const uint32_t S = s->sub_steps;
+    uint32_t done = 0;
+    // the first substep after circles/polygons were added with a pending acc runs eagerly with the
+    // accel variant of K1 (particle.rs:23-24); afterwards acc == 0 and gravity is fused.
+    if (s->accel_pending) {
+        if (int rc = launch_substep()) return rc;
+        s->accel_pending = false;
+        drop_graph();
+        for (uint32_t k = 1; k < S; k++)
+            if (int rc = launch_substep()) return rc;
+        done = 1;
+    }
+    if (done == updates) return BENDY_OK;
+    if (s->profiling) {
+        for (uint32_t u = done; u < updates; u++)
+            for (uint32_t k = 0; k < S; k++)
+                if (int rc = launch_substep()) return rc;
+        return BENDY_OK;
+    }
+    if (!s->graph_exec || s->graph_substeps != S)
+        if (int rc = build_graph(S)) return rc;
+    for (uint32_t u = done; u < updates; u++) {
+        CK(cudaGraphLaunch(s->graph_exec, s->stream));
+        s->launches += (uint64_t)s->kernels_per_substep * S;
+    }
+    return BENDY_OK;
+}
+
+}  // namespace
+
+bendy_solver::~bendy_solver() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (PendingEvent &pe : pending) {
+        cudaEventDestroy(pe.e0);
+        cudaEventDestroy(pe.e1);
+    }
+    for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
+    if (t0) cudaEventDestroy(t0);
+    if (t1) cudaEventDestroy(t1);
+    if (h_prm_ring) {
+        for (uint32_t i = 0; i < kPrmRing; i++)
+            if (prm_ring_ev[i]) cudaEventDestroy(prm_ring_ev[i]);
+        cudaFreeHost(h_prm_ring);
+    }
+    if (stream) cudaStreamDestroy(stream);
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+#undef CK
+// inside the extern "C" functions (an `ops` local is in scope)
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) return ops.fail_cuda(_e, #call, __LINE__);                             \
+    } while (0)
+#define OPS Ops ops{s}
+#define NEED(s)                                     \
+    if (!(s)) {                                     \
+        g_last_error = "null solver handle";        \
+        return BENDY_ERR_ARG;                       \
+    }
+
+extern "C" {
+
+int bendy_abi_version(void) { return BENDY_ABI_VERSION; }
+
+const char *bendy_last_error(const bendy_solver *s) { return s ? s->err.c_str() : g_last_error.c_str(); }
+
+bendy_solver *bendy_create(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_last_error = std::string("no CUDA device (") + cudaGetErrorString(e) +
+                       "): libbendy2d_b200 has no CPU path";
+        return nullptr;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) {
+        g_last_error = "device index out of range";
+        return nullptr;
+    }
+    std::unique_ptr<bendy_solver> s(new bendy_solver());
+    s->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&s->t0)) != cudaSuccess || (e = cudaEventCreate(&s->t1)) != cudaSuccess) {
+        g_last_error = std::string("CUDA init failed: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    return s.release();
+}
+
+void bendy_destroy(bendy_solver *s) { delete s; }
+
+bendy_solver *bendy_clone(bendy_solver *s) {
+    if (!s) return nullptr;
+    OPS;
+    if (ops.bind() || ops.pull()) return nullptr;
+    bendy_solver *c = bendy_create(s->device);
+    if (!c) return nullptr;
+    c->p_pos = s->p_pos, c->p_prev = s->p_prev, c->p_k = s->p_k;
+    c->c_pos = s->c_pos, c->c_prev = s->c_prev, c->c_acc = s->c_acc, c->c_rad = s->c_rad, c->c_k = s->c_k;
+    c->pl_ab = s->pl_ab, c->pl_len = s->pl_len, c->cl = s->cl;
+    c->polys = s->polys, c->g_pos = s->g_pos, c->g_prev = s->g_prev, c->g_acc = s->g_acc;
+    c->gl_ab = s->gl_ab, c->gl_len = s->gl_len, c->any_acc = s->any_acc;
+    c->sub_steps = s->sub_steps, c->particle_radius = s->particle_radius, c->grid_cell = s->grid_cell;
+    c->polygon_contact = s->polygon_contact, c->plan_params = s->plan_params;
+    return c;
+}
+
+// ---- scene construction --------------------------------------------------------------------
+static int edit_begin(bendy_solver *s) {
+    OPS;
+    if (s->sticky != BENDY_OK) return ops.fail(s->sticky, s->err);
+    if (!s->host_valid) {
+        if (int rc = ops.pull()) return rc;
+    }
+    return BENDY_OK;
+}
+static void edit_end(bendy_solver *s) {
+    s->topo_dirty = true;
+    s->device_valid = false;
+}
+
+int bendy_add_particles(bendy_solver *s, const float *pos_xy, size_t n) {
+    NEED(s);
+    OPS;
+    if (n && !pos_xy) return ops.fail(BENDY_ERR_ARG, "bendy_add_particles: null positions");
+    if (s->p_pos.size() + n > 0x7FFFFFF0u) return ops.fail(BENDY_ERR_ARG, "too many particles");
+    if (int rc = edit_begin(s)) return rc;
+    for (size_t i = 0; i < n; i++) {
+        float2 p = make_float2(pos_xy[2 * i], pos_xy[2 * i + 1]);
+        s->p_pos.push_back(p);
+        s->p_prev.push_back(p);  // particle.rs:15
+    }
+    if (!s->p_k.empty()) s->p_k.resize(s->p_pos.size(), 1.0f);
+    edit_end(s);
+    return BENDY_OK;
+}
+
+int bendy_add_circles(bendy_solver *s, const float *pos_xy, const float *prev_xy, const float *acc_xy,
+                      const float *radius, size_t n) {
+    NEED(s);
+    OPS;
+    if (n && (!pos_xy || !radius)) return ops.fail(BENDY_ERR_ARG, "bendy_add_circles: null positions or radii");
+    if (int rc = edit_begin(s)) return rc;
+    for (size_t i = 0; i < n; i++) {
+        float2 p = make_float2(pos_xy[2 * i], pos_xy[2 * i + 1]);
+        s->c_pos.push_back(p);
+        s->c_prev.push_back(prev_xy ? make_float2(prev_xy[2 * i], prev_xy[2 * i + 1]) : p);
+        float2 a = acc_xy ? make_float2(acc_xy[2 * i], acc_xy[2 * i + 1]) : make_float2(0.f, 0.f);
+        if (a.x != 0.f || a.y != 0.f) s->any_acc = true;
+        s->c_acc.push_back(a);
+        s->c_rad.push_back(radius[i]);
+    }
+    if (!s->c_k.empty()) s->c_k.resize(s->c_pos.size(), 1.0f);
+    edit_end(s);
+    return BENDY_OK;
+}
+
+int bendy_add_polygon(bendy_solver *s, const float *pos_xy, const float *prev_xy, const float *acc_xy, size_t nv,
+                      const uint32_t *link_ab, const float *link_len, size_t nl, int is_static, float cx, float cy) {
+    NEED(s);
+    OPS;
+    if (nv == 0 || !pos_xy) return ops.fail(BENDY_ERR_ARG, "bendy_add_polygon: no points");
+    if (nl && (!link_ab || !link_len)) return ops.fail(BENDY_ERR_ARG, "bendy_add_polygon: null links");
+    for (size_t k = 0; k < nl; k++)  // link.rs:19-21 on the polygon's own particle vector
+        if (!(link_ab[2 * k] < link_ab[2 * k + 1]) || !(link_ab[2 * k + 1] < nv))
+            return ops.fail(BENDY_ERR_LINK, "bendy_add_polygon: link needs a < b < point count (the reference panics)");
+    if (int rc = edit_begin(s)) return rc;
+    PolyHost P;
+    P.start = (uint32_t)s->g_pos.size();
+    P.nv = (uint32_t)nv;
+    P.link_start = (uint32_t)s->gl_len.size();
+    P.nl = (uint32_t)nl;
+    P.is_static = is_static != 0;
+    P.center = make_float2(cx, cy);
+    for (size_t i = 0; i < nv; i++) {
+        float2 p = make_float2(pos_xy[2 * i], pos_xy[2 * i + 1]);
+        s->g_pos.push_back(p);
+        s->g_prev.push_back(prev_xy ? make_float2(prev_xy[2 * i], prev_xy[2 * i + 1]) : p);
+        float2 a = acc_xy ? make_float2(acc_xy[2 * i], acc_xy[2 * i + 1]) : make_float2(0.f, 0.f);
+        if ((a.x != 0.f || a.y != 0.f) && !P.is_static) s->any_acc = true;
+        s->g_acc.push_back(a);
+    }
+    for (size_t k = 0; k < nl; k++) {
+        s->gl_ab.push_back(link_ab[2 * k]);
+        s->gl_ab.push_back(link_ab[2 * k + 1]);
+        s->gl_len.push_back(link_len[k]);
+    }
+    s->polys.push_back(P);
+    edit_end(s);
+    return BENDY_OK;
+}
+
+int bendy_add_particle_links(bendy_solver *s, const uint32_t *ab, const float *len, size_t n) {
+    NEED(s);
+    OPS;
+    if (n && (!ab || !len)) return ops.fail(BENDY_ERR_ARG, "bendy_add_particle_links: null arrays");
+    const size_t np = s->p_pos.size();
+    for (size_t k = 0; k < n; k++)
+        if (!(ab[2 * k] < ab[2 * k + 1]) || !(ab[2 * k + 1] < np))
+            return ops.fail(BENDY_ERR_LINK,
+                            "bendy_add_particle_links: link needs a < b < particle count (the reference panics, "
+                            "link.rs:19-21)");
+    if (int rc = edit_begin(s)) return rc;
+    s->pl_ab.insert(s->pl_ab.end(), ab, ab + 2 * n);
+    s->pl_len.insert(s->pl_len.end(), len, len + n);
+    edit_end(s);
+    return BENDY_OK;
+}
+
+int bendy_add_circle_links(bendy_solver *s, const uint32_t *ab, const float *len, size_t n) {
+    NEED(s);
+    OPS;
+    if (n && (!ab || !len)) return ops.fail(BENDY_ERR_ARG, "bendy_add_circle_links: null arrays");
+    const size_t nc = s->c_pos.size();
+    for (size_t k = 0; k < n; k++)
+        if (!(ab[2 * k] < ab[2 * k + 1]) || !(ab[2 * k + 1] < nc))
+            return ops.fail(BENDY_ERR_LINK, "bendy_add_circle_links: link needs a < b < circle count (the reference panics)");
+    if (int rc = edit_begin(s)) return rc;
+    for (size_t k = 0; k < n; k++) s->cl.push_back(GlobalLink{ab[2 * k], ab[2 * k + 1], len[k]});
+    edit_end(s);
+    return BENDY_OK;
+}
+
+// ---- hot path ---------------------------------------------------------------------------------
+int bendy_update_n(bendy_solver *s, uint32_t n, float dt, float gx, float gy, float bx, float by, float bw,
+                   float bh) {
+    NEED(s);
+    OPS;
+    if (n == 0) return BENDY_OK;
+    if (int rc = ops.ensure_ready()) return rc;
+    // solver.rs:107-108
+    float mult = 1.0f / (float)s->sub_steps;
+    float delta = dt * mult;
+    if (int rc = ops.configure(delta, gx, gy, bx, by, bw, bh)) return rc;
+    if (int rc = ops.enqueue_substeps(n)) return rc;
+    s->host_valid = false;
+    return BENDY_OK;
+}
+
+int bendy_update(bendy_solver *s, float dt, float gx, float gy, float bx, float by, float bw, float bh) {
+    return bendy_update_n(s, 1, dt, gx, gy, bx, by, bw, bh);
+}
+
+int bendy_synchronize(bendy_solver *s) {
+    NEED(s);
+    OPS;
+    if (s->sticky != BENDY_OK) return ops.fail(s->sticky, s->err);
+    if (!s->stream) return BENDY_OK;
+    if (int rc = ops.bind()) return rc;
+    if (int rc = ops.flush_events()) return rc;
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) return ops.fail_cuda(e, "cudaStreamSynchronize", __LINE__);
+    return ops.check_flags();
+}
+
+// ---- getters ------------------------------------------------------------------------------------
+size_t bendy_particle_len(const bendy_solver *s) { return s ? s->p_pos.size() : 0; }
+size_t bendy_circle_len(const bendy_solver *s) { return s ? s->c_pos.size() : 0; }
+size_t bendy_polygon_len(const bendy_solver *s) { return s ? s->polys.size() : 0; }
+size_t bendy_particle_link_len(const bendy_solver *s) { return s ? s->pl_len.size() : 0; }
+size_t bendy_circle_link_len(const bendy_solver *s) { return s ? s->cl.size() : 0; }
+size_t bendy_polygon_point_len(const bendy_solver *s, size_t k) { return s && k < s->polys.size() ? s->polys[k].nv : 0; }
+size_t bendy_polygon_link_len(const bendy_solver *s, size_t k) { return s && k < s->polys.size() ? s->polys[k].nl : 0; }
+
+static void copy_out(const std::vector<float2> &v, size_t first, size_t n, float *out) {
+    if (out && n) std::memcpy(out, v.data() + first, n * sizeof(float2));
+}
+
+int bendy_read_particles(bendy_solver *s, size_t first, size_t n, float *pos_xy, float *prev_xy) {
+    NEED(s);
+    OPS;
+    if (first + n > s->p_pos.size()) return ops.fail(BENDY_ERR_ARG, "bendy_read_particles: range out of bounds");
+    if (n == 0) return BENDY_OK;
+    if (s->host_valid) {
+        copy_out(s->p_pos, first, n, pos_xy);
+        copy_out(s->p_prev, first, n, prev_xy);
+        return BENDY_OK;
+    }
+    // device is authoritative: gather USER order on the device, copy straight into the caller's buffers
+    if (int rc = ops.ensure_ready()) return rc;
+    if (int rc = ops.flush_events()) return rc;
+    for (int which = 0; which < 2; which++) {
+        float *out = which == 0 ? pos_xy : prev_xy;
+        if (!out) continue;
+        const float2 *src = which == 0 ? s->d_pos.p : s->d_prev.p;
+        k_gather<<<cdiv((uint32_t)n, 256), 256, 0, s->stream>>>(src, s->d_rank.p + first, (uint32_t)n, s->d_stage.p);
+        s->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, s->d_stage.p, n * sizeof(float2), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    return ops.check_flags();
+}
+
+int bendy_write_particles(bendy_solver *s, size_t first, size_t n, const float *pos_xy, const float *prev_xy) {
+    NEED(s);
+    OPS;
+    if (first + n > s->p_pos.size()) return ops.fail(BENDY_ERR_ARG, "bendy_write_particles: range out of bounds");
+    if (n == 0) return BENDY_OK;
+    if (s->topo_dirty || !s->device_valid) {  // nothing on the device yet: edit the host scene
+        if (int rc = edit_begin(s)) return rc;
+        if (pos_xy) std::memcpy(s->p_pos.data() + first, pos_xy, n * sizeof(float2));
+        if (prev_xy) std::memcpy(s->p_prev.data() + first, prev_xy, n * sizeof(float2));
+        s->device_valid = false;
+        return BENDY_OK;
+    }
+    if (int rc = ops.ensure_ready()) return rc;
+    for (int which = 0; which < 2; which++) {
+        const float *in = which == 0 ? pos_xy : prev_xy;
+        if (!in) continue;
+        float2 *dst = which == 0 ? s->d_pos.p : s->d_prev.p;
+        CK(cudaMemcpyAsync(s->d_stage.p, in, n * sizeof(float2), cudaMemcpyHostToDevice, s->stream));
+        k_scatter<<<cdiv((uint32_t)n, 256), 256, 0, s->stream>>>(s->d_stage.p, s->d_rank.p + first, (uint32_t)n, dst);
+        s->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s->stream));  // the caller's buffer may be reused after return
+    }
+    s->host_valid = false;
+    return BENDY_OK;
+}
+
+int bendy_read_circles(bendy_solver *s, size_t first, size_t n, float *pos_xy, float *prev_xy, float *radius) {
+    NEED(s);
+    OPS;
+    if (first + n > s->c_pos.size()) return ops.fail(BENDY_ERR_ARG, "bendy_read_circles: range out of bounds");
+    if (n == 0) return BENDY_OK;
+    if (radius) std::memcpy(radius, s->c_rad.data() + first, n * sizeof(float));
+    if (s->host_valid) {
+        copy_out(s->c_pos, first, n, pos_xy);
+        copy_out(s->c_prev, first, n, prev_xy);
+        return BENDY_OK;
+    }
+    if (int rc = ops.ensure_ready()) return rc;
+    if (int rc = ops.flush_events()) return rc;
+    if (pos_xy)
+        CK(cudaMemcpyAsync(pos_xy, s->d_pos.p + s->nP + first, n * sizeof(float2), cudaMemcpyDeviceToHost, s->stream));
+    if (prev_xy)
+        CK(cudaMemcpyAsync(prev_xy, s->d_prev.p + s->nP + first, n * sizeof(float2), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return ops.check_flags();
+}
+
+int bendy_read_polygon(bendy_solver *s, size_t k, float *pos_xy, float *prev_xy, float *center_xy, int *is_static) {
+    NEED(s);
+    OPS;
+    if (k >= s->polys.size()) return ops.fail(BENDY_ERR_ARG, "bendy_read_polygon: index out of bounds");
+    if (!s->host_valid) {
+        if (int rc = ops.ensure_ready()) return rc;
+        if (int rc = ops.flush_events()) return rc;
+        if (int rc = ops.pull()) return rc;
+    }
+    const PolyHost &P = s->polys[k];
+    copy_out(s->g_pos, P.start, P.nv, pos_xy);
+    copy_out(s->g_prev, P.start, P.nv, prev_xy);
+    if (center_xy) center_xy[0] = P.center.x, center_xy[1] = P.center.y;
+    if (is_static) *is_static = P.is_static ? 1 : 0;
+    return BENDY_OK;
+}
+
+int bendy_read_particle_links(const bendy_solver *s, size_t first, size_t n, uint32_t *ab, float *len) {
+    if (!s || first + n > s->pl_len.size()) return BENDY_ERR_ARG;
+    if (ab && n) std::memcpy(ab, s->pl_ab.data() + 2 * first, 2 * n * sizeof(uint32_t));
+    if (len && n) std::memcpy(len, s->pl_len.data() + first, n * sizeof(float));
+    return BENDY_OK;
+}
+int bendy_read_circle_links(const bendy_solver *s, size_t first, size_t n, uint32_t *ab, float *len) {
+    if (!s || first + n > s->cl.size()) return BENDY_ERR_ARG;
+    for (size_t k = 0; k < n; k++) {
+        if (ab) ab[2 * k] = s->cl[first + k].a, ab[2 * k + 1] = s->cl[first + k].b;
+        if (len) len[k] = s->cl[first + k].len;
+    }
+    return BENDY_OK;
+}
+int bendy_read_polygon_links(const bendy_solver *s, size_t k, uint32_t *ab, float *len) {
+    if (!s || k >= s->polys.size()) return BENDY_ERR_ARG;
+    const PolyHost &P = s->polys[k];
+    if (ab && P.nl) std::memcpy(ab, s->gl_ab.data() + 2 * (size_t)P.link_start, 2 * (size_t)P.nl * sizeof(uint32_t));
+    if (len && P.nl) std::memcpy(len, s->gl_len.data() + P.link_start, (size_t)P.nl * sizeof(float));
+    return BENDY_OK;
+}
+
+// ---- additive API -----------------------------------------------------------------------------
+int bendy_set_sub_steps(bendy_solver *s, uint16_t n) {
+    NEED(s);
+    OPS;
+    if (n == 0) return ops.fail(BENDY_ERR_ARG, "sub_steps must be >= 1");
+    s->sub_steps = n;
+    return BENDY_OK;
+}
+int bendy_set_particle_radius(bendy_solver *s, float r) {
+    NEED(s);
+    OPS;
+    if (!(r >= 0.f)) return ops.fail(BENDY_ERR_ARG, "particle radius must be >= 0");
+    if (r != s->particle_radius) {
+        s->particle_radius = r;
+        s->prm_valid = false;
+        ops.drop_graph();
+    }
+    return BENDY_OK;
+}
+int bendy_set_grid_cell(bendy_solver *s, float h) {
+    NEED(s);
+    OPS;
+    if (!(h >= 0.f)) return ops.fail(BENDY_ERR_ARG, "grid cell must be >= 0");
+    if (h != s->grid_cell) {
+        s->grid_cell = h;
+        s->prm_valid = false;
+        ops.drop_graph();
+    }
+    return BENDY_OK;
+}
+int bendy_set_polygon_contact(bendy_solver *s, int on) {
+    NEED(s);
+    OPS;
+    if ((on != 0) != s->polygon_contact) {
+        s->polygon_contact = on != 0;
+        s->prm_valid = false;
+        ops.drop_graph();
+    }
+    return BENDY_OK;
+}
+int bendy_set_particle_inv_mass(bendy_solver *s, size_t first, size_t n, const float *k) {
+    NEED(s);
+    OPS;
+    if (first + n > s->p_pos.size() || (n && !k)) return ops.fail(BENDY_ERR_ARG, "bendy_set_particle_inv_mass: bad range");
+    for (size_t i = 0; i < n; i++)
+        if (!(k[i] >= 0.f)) return ops.fail(BENDY_ERR_ARG, "inverse-mass scale must be >= 0");
+    if (int rc = edit_begin(s)) return rc;
+    if (s->p_k.empty()) s->p_k.assign(s->p_pos.size(), 1.0f);
+    std::copy(k, k + n, s->p_k.begin() + first);
+    edit_end(s);
+    return BENDY_OK;
+}
+int bendy_set_circle_inv_mass(bendy_solver *s, size_t first, size_t n, const float *k) {
+    NEED(s);
+    OPS;
+    if (first + n > s->c_pos.size() || (n && !k)) return ops.fail(BENDY_ERR_ARG, "bendy_set_circle_inv_mass: bad range");
+    for (size_t i = 0; i < n; i++)
+        if (!(k[i] >= 0.f)) return ops.fail(BENDY_ERR_ARG, "inverse-mass scale must be >= 0");
+    if (int rc = edit_begin(s)) return rc;
+    if (s->c_k.empty()) s->c_k.assign(s->c_pos.size(), 1.0f);
+    std::copy(k, k + n, s->c_k.begin() + first);
+    edit_end(s);
+    return BENDY_OK;
+}
+int bendy_set_plan_params(bendy_solver *s, uint32_t pack_points, uint32_t max_points) {
+    NEED(s);
+    if (pack_points) s->plan_params.pack_points = pack_points;
+    if (max_points) s->plan_params.max_points = max_points;
+    s->topo_dirty = true;
+    return BENDY_OK;
+}
+
+// ---- schedule export ----------------------------------------------------------------------------
+static void fill_info(const LinkPlan &P, const LinkPlan *G, bendy_schedule_info *out) {
+    std::memset(out, 0, sizeof *out);
+    out->n_partitions = P.n_parts();
+    out->n_local_colours = P.n_local_colours;
+    out->n_global_colours = P.n_global_colours();
+    out->n_local_links = (uint32_t)P.local_links.size();
+    out->n_global_links = (uint32_t)P.global_links.size();
+    if (G) out->n_poly_partitions = G->n_parts();
+}
+
+int bendy_get_schedule_info(bendy_solver *s, bendy_schedule_info *out) {
+    NEED(s);
+    OPS;
+    if (!out) return ops.fail(BENDY_ERR_ARG, "null out");
+    if (int rc = ops.ensure_ready()) return rc;
+    fill_info(s->plan_p, &s->plan_g, out);
+    out->kernels_per_substep = s->kernels_per_substep;
+    return BENDY_OK;
+}
+int bendy_get_link_order(bendy_solver *s, uint32_t *perm, size_t n) {
+    NEED(s);
+    OPS;
+    if (n != s->pl_len.size() || (n && !perm)) return ops.fail(BENDY_ERR_ARG, "bendy_get_link_order: n must equal the link count");
+    if (int rc = ops.ensure_ready()) return rc;
+    std::vector<uint32_t> p = s->plan_p.perm();
+    std::copy(p.begin(), p.end(), perm);
+    return BENDY_OK;
+}
+int bendy_get_point_rank(bendy_solver *s, uint32_t *rank, size_t n) {
+    NEED(s);
+    OPS;
+    if (n != s->p_pos.size() || (n && !rank)) return ops.fail(BENDY_ERR_ARG, "bendy_get_point_rank: n must equal the particle count");
+    if (int rc = ops.ensure_ready()) return rc;
+    std::copy(s->plan_p.rank.begin(), s->plan_p.rank.end(), rank);
+    return BENDY_OK;
+}
+int bendy_get_grid(bendy_solver *s, float bx, float by, float bw, float bh, float *ox, float *oy, float *inv_h,
+                   int *nx, int *ny) {
+    NEED(s);
+    OPS;
+    StepParams p{};
+    uint32_t nc = 0;
+    ops.grid_for(bx, by, bw, bh, &p, &nc);
+    if (ox) *ox = p.gox;
+    if (oy) *oy = p.goy;
+    if (inv_h) *inv_h = p.inv_h;
+    if (nx) *nx = p.nx;
+    if (ny) *ny = p.ny;
+    return BENDY_OK;
+}
+
+// ---- measurement ----------------------------------------------------------------------------------
+int bendy_set_profiling(bendy_solver *s, int profile) {
+    NEED(s);
+    OPS;
+    if (int rc = ops.flush_events()) return rc;
+    s->profiling = profile != 0;
+    return BENDY_OK;
+}
+int bendy_get_kernel_times(bendy_solver *s, double *ms, uint64_t *launches, int n_classes, int reset) {
+    NEED(s);
+    OPS;
+    if (int rc = ops.bind()) return rc;
+    if (int rc = ops.flush_events()) return rc;
+    for (int k = 0; k < n_classes && k < BENDY_K_CLASSES; k++) {
+        if (ms) ms[k] = s->k_ms[k];
+        if (launches) launches[k] = s->k_launches[k];
+    }
+    if (reset) {
+        std::memset(s->k_ms, 0, sizeof s->k_ms);
+        std::memset(s->k_launches, 0, sizeof s->k_launches);
+    }
+    return BENDY_OK;
+}
+uint64_t bendy_launch_count(const bendy_solver *s) { return s ? s->launches : 0; }
+
+int bendy_timer_start(bendy_solver *s) {
+    NEED(s);
+    OPS;
+    if (int rc = ops.bind()) return rc;
+    CK(cudaEventRecord(s->t0, s->stream));
+    return BENDY_OK;
+}
+int bendy_timer_stop(bendy_solver *s, float *ms) {
+    NEED(s);
+    OPS;
+    if (int rc = ops.bind()) return rc;
+    CK(cudaEventRecord(s->t1, s->stream));
+    CK(cudaEventSynchronize(s->t1));
+    float v = 0.f;
+    CK(cudaEventElapsedTime(&v, s->t0, s->t1));
+    if (ms) *ms = v;
+    return BENDY_OK;
+}
+void *bendy_get_stream(const bendy_solver *s) { return s ? (void *)s->stream : nullptr; }
+int bendy_get_device(const bendy_solver *s) { return s ? s->device : -1; }
+
+int bendy_get_device_buffers(bendy_solver *s, void **pos, void **prev, size_t *n_points) {
+    NEED(s);
+    OPS;
+    if (int rc = ops.ensure_ready()) return rc;
+    if (pos) *pos = s->d_pos.p;
+    if (prev) *prev = s->d_prev.p;
+    if (n_points) *n_points = s->N;
+    return BENDY_OK;
+}
+
+// ---- host-only planning ----------------------------------------------------------------------------
+int bendy_plan_links(size_t n_points, const uint32_t *ab, size_t n_links, uint32_t pack_points, uint32_t max_points,
+                     uint32_t *rank, uint32_t *perm, uint32_t *link_colour, uint32_t *link_partition,
+                     bendy_schedule_info *info) {
+    if (n_links && !ab) return BENDY_ERR_ARG;
+    for (size_t k = 0; k < n_links; k++)
+        if (!(ab[2 * k] < ab[2 * k + 1]) || !(ab[2 * k + 1] < n_points)) {
+            g_last_error = "bendy_plan_links: link needs a < b < n_points";
+            return BENDY_ERR_LINK;
+        }
+    PlanParams pp;
+    if (pack_points) pp.pack_points = pack_points;
+    if (max_points) pp.max_points = max_points;
+    std::vector<float> len(n_links, 1.0f);
+    LinkPlan P;
+    std::string err;
+    if (!plan_links(n_points, ab, len.data(), n_links, pp, false, &P, &err)) {
+        g_last_error = err;
+        return BENDY_ERR_UNSUPPORTED;
+    }
+    if (rank) std::copy(P.rank.begin(), P.rank.end(), rank);
+    if (perm) {
+        std::vector<uint32_t> p = P.perm();
+        std::copy(p.begin(), p.end(), perm);
+    }
+    if (link_colour || link_partition) {
+        const size_t stride = (size_t)P.n_local_colours + 1;
+        for (uint32_t p = 0; p < P.n_parts(); p++)
+            for (uint32_t c = 0; c < P.n_local_colours; c++)
+                for (uint32_t l = P.part_colour_start[p * stride + c]; l < P.part_colour_start[p * stride + c + 1]; l++) {
+                    if (link_colour) link_colour[P.local_user[l]] = c;
+                    if (link_partition) link_partition[P.local_user[l]] = p;
+                }
+        for (uint32_t c = 0; c < P.n_global_colours(); c++)
+            for (uint32_t l = P.gcolour_start[c]; l < P.gcolour_start[c + 1]; l++) {
+                if (link_colour) link_colour[P.global_user[l]] = P.n_local_colours + c;
+                if (link_partition) link_partition[P.global_user[l]] = 0xFFFFFFFFu;
+            }
+    }
+    if (info) fill_info(P, nullptr, info);
+    return BENDY_OK;
+}
+
+}  // extern "C"

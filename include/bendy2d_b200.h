@@ -1,0 +1,180 @@
+/*
+ * bendy2d_b200.h — C ABI of libbendy2d_b200.so: the B200 (sm_100a) solver substep behind
+ * bendy2d's public `Solver` API.
+ *
+ * The reference (Murrent/bendy2d, Rust) has no FFI; its boundary for this path is the public
+ * API of `Solver` in src/solver.rs.  Each entry point below names the reference item it replaces
+ * (file:line relative to the reference repo).  A Rust `bendy2d-sys` crate binds exactly these
+ * symbols (see INTEGRATION.md and rust/).
+ *
+ * Conventions
+ *  - plain C types only; every pointer is caller-owned HOST memory, copied before return;
+ *  - xy arrays are interleaved f32 pairs (x0,y0,x1,y1,...) — the layout of nalgebra Vector2<f32>;
+ *  - int return: BENDY_OK or a negative error; bendy_last_error() gives the text;
+ *  - a handle is bound to ONE CUDA device and ONE stream; thread-compatible, not thread-safe
+ *    (the reference takes &mut self for every mutation: solver.rs:52-67,106);
+ *  - bendy_update() only enqueues work; reads synchronise.  There is NO CPU fallback: without a
+ *    CUDA device bendy_create() fails.
+ */
+#ifndef BENDY2D_B200_H
+#define BENDY2D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BENDY_ABI_VERSION 1
+
+typedef struct bendy_solver bendy_solver;
+
+enum {
+    BENDY_OK = 0,
+    BENDY_ERR_ARG = -1,         /* null pointer / out-of-range argument */
+    BENDY_ERR_LINK = -2,        /* link with a >= b or b >= len: the reference panics (link.rs:19-21) */
+    BENDY_ERR_CUDA = -3,        /* CUDA runtime error (sticky; text in bendy_last_error) */
+    BENDY_ERR_UNSUPPORTED = -4, /* scene outside what the device path implements */
+    BENDY_ERR_NO_DEVICE = -5    /* no CUDA device: there is no CPU path */
+};
+
+/* ---------------------------------------------------------------- lifetime */
+/* Solver::new (solver.rs:34-50).  device < 0 = the calling thread's current device.
+ * Returns NULL on failure (bendy_last_error(NULL) has the reason). */
+bendy_solver *bendy_create(int device);
+void bendy_destroy(bendy_solver *s);
+/* #[derive(Clone)] on Solver (solver.rs:19): deep copy of host tables and device buffers. */
+bendy_solver *bendy_clone(bendy_solver *s);
+const char *bendy_last_error(const bendy_solver *s);
+int bendy_abi_version(void);
+
+/* ---------------------------------------------------------------- scene construction */
+/* Solver::add_particle (solver.rs:52-54) x n: Particle::new => prev=pos, acc=0 (particle.rs:12-18) */
+int bendy_add_particles(bendy_solver *s, const float *pos_xy, size_t n);
+/* Solver::add_circle (solver.rs:55-57) x n. prev_xy NULL => prev=pos; acc_xy NULL => 0 */
+int bendy_add_circles(bendy_solver *s, const float *pos_xy, const float *prev_xy, const float *acc_xy,
+                      const float *radius, size_t n);
+/* Solver::add_polygon (solver.rs:58-60): points, polygon-local links (a<b), is_static, cached centre
+ * (polygon.rs:8-14). */
+int bendy_add_polygon(bendy_solver *s, const float *pos_xy, const float *prev_xy, const float *acc_xy, size_t nv,
+                      const uint32_t *link_ab, const float *link_len, size_t nl, int is_static, float cx, float cy);
+/* Solver::add_particle_link (solver.rs:62-64) x n; ab = (a0,b0,a1,b1,...).  Validates a<b<len at
+ * add time and returns BENDY_ERR_LINK where the reference would panic inside update. */
+int bendy_add_particle_links(bendy_solver *s, const uint32_t *ab, const float *len, size_t n);
+/* Solver::add_circle_link (solver.rs:65-67) x n */
+int bendy_add_circle_links(bendy_solver *s, const uint32_t *ab, const float *len, size_t n);
+
+/* ---------------------------------------------------------------- the hot path */
+/* Solver::update(dt) (solver.rs:106-116).  The pub fields gravity and bounds (solver.rs:21-22) are
+ * passed by value on every call because the user may mutate them between calls.  bounds_active
+ * is never read by the reference (solver.rs:155-165) so it is not passed.  Asynchronous. */
+int bendy_update(bendy_solver *s, float dt, float gx, float gy, float bx, float by, float bw, float bh);
+/* n back-to-back update(dt) calls in one enqueue (same arithmetic as calling bendy_update n times) */
+int bendy_update_n(bendy_solver *s, uint32_t n, float dt, float gx, float gy, float bx, float by, float bw,
+                   float bh);
+int bendy_synchronize(bendy_solver *s);
+
+/* ---------------------------------------------------------------- getters */
+size_t bendy_particle_len(const bendy_solver *s);      /* get_particle_len solver.rs:69 */
+size_t bendy_circle_len(const bendy_solver *s);        /* get_circles_len  solver.rs:72 */
+size_t bendy_polygon_len(const bendy_solver *s);       /* get_polygons_len solver.rs:75 */
+size_t bendy_particle_link_len(const bendy_solver *s); /* get_particle_links().len() solver.rs:79 */
+size_t bendy_circle_link_len(const bendy_solver *s);   /* get_circle_links().len()   solver.rs:82 */
+size_t bendy_polygon_point_len(const bendy_solver *s, size_t polygon);
+size_t bendy_polygon_link_len(const bendy_solver *s, size_t polygon);
+/* get_particles / get_particle (solver.rs:86,96): copies [first, first+n) in USER order; any pointer may be NULL */
+int bendy_read_particles(bendy_solver *s, size_t first, size_t n, float *pos_xy, float *prev_xy);
+/* get_circles / get_circle (solver.rs:89,99) */
+int bendy_read_circles(bendy_solver *s, size_t first, size_t n, float *pos_xy, float *prev_xy, float *radius);
+/* get_polygons / get_polygon (solver.rs:92,102): points, cached centre, static flag */
+int bendy_read_polygon(bendy_solver *s, size_t polygon, float *pos_xy, float *prev_xy, float *center_xy,
+                       int *is_static);
+int bendy_read_particle_links(const bendy_solver *s, size_t first, size_t n, uint32_t *ab, float *len);
+int bendy_read_circle_links(const bendy_solver *s, size_t first, size_t n, uint32_t *ab, float *len);
+int bendy_read_polygon_links(const bendy_solver *s, size_t polygon, uint32_t *ab, float *len);
+
+/* ---------------------------------------------------------------- additive API (not in the reference) */
+/* sub_steps is a private field fixed at 1 in the reference (solver.rs:29,47); default 1 */
+int bendy_set_sub_steps(bendy_solver *s, uint16_t n);
+/* overwrite pos/prev of free particles [first, first+n) from host buffers (snapshot restore / streaming) */
+int bendy_write_particles(bendy_solver *s, size_t first, size_t n, const float *pos_xy, const float *prev_xy);
+/* ext: r > 0 makes every free particle a disc of radius r that collides with particles and Circles
+ * through the uniform-grid narrowphase; 0 (default) = reference semantics (no particle contact) */
+int bendy_set_particle_radius(bendy_solver *s, float r);
+/* ext: grid cell edge; 0 = auto (2*r rounded up so the cell count stays bounded) */
+int bendy_set_grid_cell(bendy_solver *s, float h);
+/* ext: free particles vs static convex polygons (closest-edge contact); default off */
+int bendy_set_polygon_contact(bendy_solver *s, int on);
+/* ext: inverse-mass scale per particle / circle; default 1 (= reference arithmetic); 0 pins the point */
+int bendy_set_particle_inv_mass(bendy_solver *s, size_t first, size_t n, const float *k);
+int bendy_set_circle_inv_mass(bendy_solver *s, size_t first, size_t n, const float *k);
+/* planner knobs: points per shared-memory partition (pack target, hard cap); 0 keeps the default */
+int bendy_set_plan_params(bendy_solver *s, uint32_t pack_points, uint32_t max_points);
+
+/* ---------------------------------------------------------------- schedule export (parity replay) */
+typedef struct bendy_schedule_info {
+    uint32_t n_partitions;      /* shared-memory link partitions (free particles) */
+    uint32_t n_local_colours;   /* max colours inside one partition */
+    uint32_t n_global_colours;  /* colours of cross-partition links (one launch each) */
+    uint32_t n_local_links;
+    uint32_t n_global_links;
+    uint32_t n_poly_partitions; /* partitions holding polygon-internal links */
+    uint32_t kernels_per_substep;
+    uint32_t reserved;
+} bendy_schedule_info;
+/* Builds the schedule if links changed, then reports it. */
+int bendy_get_schedule_info(bendy_solver *s, bendy_schedule_info *out);
+/* perm[k] = user index of the k-th particle link in the sequential order that is arithmetically
+ * identical to the device's parallel schedule (feed it to the reference/oracle). n = link count */
+int bendy_get_link_order(bendy_solver *s, uint32_t *perm, size_t n);
+/* rank[i] = internal index of user particle i (fixes the in-cell accumulation order of the grid) */
+int bendy_get_point_rank(bendy_solver *s, uint32_t *rank, size_t n);
+/* the broadphase grid bendy_update would use for these bounds */
+int bendy_get_grid(bendy_solver *s, float bx, float by, float bw, float bh, float *ox, float *oy, float *inv_h,
+                   int *nx, int *ny);
+
+/* ---------------------------------------------------------------- measurement */
+enum {
+    BENDY_K_INTEGRATE = 0, /* K1 bounds + gravity + Verlet integrate */
+    BENDY_K_LINKS_LOCAL,   /* K3 shared-memory partition relaxation */
+    BENDY_K_LINKS_GLOBAL,  /* K3 cross-partition colours */
+    BENDY_K_LINKS_CIRCLE,  /* CircleLink relaxation */
+    BENDY_K_GRID_BUILD,    /* K2 hash/count/scan/scatter/canonicalise */
+    BENDY_K_NARROWPHASE,   /* K2 3x3 narrowphase */
+    BENDY_K_CIRCLES,       /* circle-circle lexicographic pass + circle binning/apply */
+    BENDY_K_POLY_PREP,     /* polygon centre / AABB / binning */
+    BENDY_K_POLY_CONTACT,  /* K4 particle-polygon closest edge (+ polygon-polygon) */
+    BENDY_K_FUSED,         /* fused integrate+links(+hash) kernel when the schedule allows it */
+    BENDY_K_CLASSES
+};
+/* profile != 0: launch kernels one by one with cudaEvent pairs (slower; for per-kernel timing).
+ * profile == 0 (default): CUDA-graph replay of the substep. */
+int bendy_set_profiling(bendy_solver *s, int profile);
+/* accumulated device ms and launch counts per kernel class since the last reset */
+int bendy_get_kernel_times(bendy_solver *s, double *ms, uint64_t *launches, int n_classes, int reset);
+/* kernels launched (graph nodes included) since creation: the gpu_launches figure of bench.py */
+uint64_t bendy_launch_count(const bendy_solver *s);
+/* cudaEvent timer on the solver's stream */
+int bendy_timer_start(bendy_solver *s);
+int bendy_timer_stop(bendy_solver *s, float *ms); /* synchronises */
+/* the cudaStream_t and device the handle runs on (for callers that interleave their own work) */
+void *bendy_get_stream(const bendy_solver *s);
+int bendy_get_device(const bendy_solver *s);
+
+/* ---------------------------------------------------------------- multi-GPU strips (halo exchange) */
+/* Device pointers of the internal SoA (pos, prev as float2 arrays in INTERNAL order) so that a host
+ * layer (torch.distributed / NCCL or CUDA IPC) can move halo particles without a host round trip. */
+int bendy_get_device_buffers(bendy_solver *s, void **pos, void **prev, size_t *n_points);
+
+/* ---------------------------------------------------------------- host-only planning (no GPU needed) */
+/* The link planner used by the solver, callable on host arrays (unit tests, offline tools).
+ * Outputs (any may be NULL): rank[n_points], perm[n_links]; info filled like bendy_get_schedule_info. */
+int bendy_plan_links(size_t n_points, const uint32_t *ab, size_t n_links, uint32_t pack_points,
+                     uint32_t max_points, uint32_t *rank, uint32_t *perm, uint32_t *link_colour,
+                     uint32_t *link_partition, bendy_schedule_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BENDY2D_B200_H */
