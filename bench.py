@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — particle-substeps/s of the bendy2d solver substep on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W [--workload c1|c2|c3|c4|c5] [--impl reference]
+
+A "step" is one frame = one Solver::update(dt) with sub_steps = 8 (8 substeps of 1/120 s; C1 uses
+its own 1/60 s x 8).  N=1 runs C3, the 1M-particle softbody field the headline target is quoted on;
+N>1 runs C5 (16M particles) sharded into spatial strips, one rank per GPU.
+Timing: CUDA events on the solver's stream, per step, L2 flushed between steps (config.l2), max
+over ranks.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SUBSTEPS_PER_STEP = 8
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def make_scene(name: str):
+    from bendy2d_b200 import scenes
+
+    sc = {"c1": scenes.c1_softbody_blob, "c2": scenes.c2_free_particles, "c3": scenes.c3_softbody_field,
+          "c4": scenes.c4_polygon_heavy, "c5": scenes.c5_softbody_field_16m}[name]()
+    if name != "c1":  # one frame = 8 substeps of 1/120 (x8 and x0.125 are exact in f32)
+        sc.dt = float(np.float32(np.float32(1.0 / 120.0) * np.float32(SUBSTEPS_PER_STEP)))
+        sc.sub_steps = SUBSTEPS_PER_STEP
+    return sc
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        # under load = upper half of the samples (the sampler also sees the idle gaps between steps)
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_sample(workload: str):
+    """Bounded sample of the workload for the CPU oracle: same construction, fewer bodies."""
+    from bendy2d_b200 import scenes
+
+    if workload == "c1":
+        sc, what = scenes.c1_softbody_blob(), "C1 in full (400 particles, 1482 links, 1 circle)"
+    elif workload == "c2":
+        sc, what = scenes.c2_free_particles(200, 100), "C2 at 20,000 discs (of 100,000), same pitch/jitter"
+    elif workload == "c4":
+        sc, what = scenes.c4_polygon_heavy(20, 400), "C4 at 8,000 discs / 400 polygons (of 200k / 10k)"
+    else:
+        sc = scenes.c3_softbody_field(20, 10, 20, 50)
+        what = "C3 construction at 200 bodies = 100,000 particles / 282,200 links / 20 circles / 50 polygons"
+    if workload != "c1":
+        sc.dt = float(np.float32(np.float32(1.0 / 120.0) * np.float32(SUBSTEPS_PER_STEP)))
+        sc.sub_steps = SUBSTEPS_PER_STEP
+    return sc, what
+
+
+def oracle_for(sc):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_from_scene
+
+    o = oracle_from_scene(sc)
+    if sc.particle_radius > 0:
+        h = 2.0 * sc.particle_radius
+        o.set_grid(sc.bounds[0], sc.bounds[1], 1.0 / h, int(np.ceil(sc.bounds[2] / h)), int(np.ceil(sc.bounds[3] / h)))
+    return o
+
+
+def time_oracle(sc, steps: int, warmup: int):
+    o = oracle_for(sc)
+    for _ in range(warmup):
+        o.update(sc.dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.update(sc.dt)
+    dt = time.perf_counter() - t0
+    return sc.n_points * sc.sub_steps * steps / dt, dt / steps * 1e3
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The Rust crate cannot be built in this image
+    (no cargo/rustc, nalgebra not vendored) so this is the oracle port: single thread, because the
+    reference is strictly single-threaded (plain for loops, no rayon: solver.rs:109-188)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workload = args.workload or ("c3" if args.gpus == 1 else "c5")
+    sc, what = cpu_baseline_sample(workload)
+    value, ms = time_oracle(sc, args.steps, args.warmup)
+    full = make_scene(workload)
+    line = {
+        "impl": "reference", "metric": "particle-substeps/s", "value": value, "unit": "particle-substeps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": full.name, "substeps_per_step": full.sub_steps, "sample": what},
+        "cpu_baseline": {"value": value, "unit": "particle-substeps/s", "cores": 1, "kind": "port",
+                         "sample": what, "host_cores_available": os.cpu_count()},
+        "e2e": {"value": value, "unit": "particle-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=25)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (not the headline)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    from bendy2d_b200 import Solver
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bendy2d_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    workload = args.workload or ("c3" if world == 1 else "c5")
+    t_build = time.perf_counter()
+    sc = make_scene(workload)
+    n_points_total = sc.n_points
+    n_warm = max(args.warmup, 3) if args.warmup else 0
+
+    def fresh_solver():
+        """every measured phase starts from the same state: initial scene + the warm-up steps"""
+        if world > 1:
+            from bendy2d_b200 import strips
+
+            sv = strips.StripSolver(sc, rank, world, local, dist)
+        else:
+            sv = Solver(local)
+            sc.load_into(sv)
+        for _ in range(n_warm):
+            sv.update(sc.dt)
+        sv.synchronize()
+        return sv
+
+    solver = fresh_solver()
+    info = solver.schedule_info()
+    log(f"[rank {rank}] scene {sc.name}: {sc.n_points} points, {sc.n_links} links, built in "
+        f"{time.perf_counter() - t_build:.1f}s; schedule {info}")
+
+    flush_buf = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        if flush_buf is not None:
+            flush_buf.zero_()
+            torch.cuda.synchronize()
+
+    # ---- timed region: K steps, each bracketed by events on the solver's stream
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = solver.launch_count()
+    barrier()
+    wall0 = time.perf_counter()
+    total_ms = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        if dist is not None:
+            dist.barrier()
+        solver.timer_start()
+        solver.update(sc.dt)
+        total_ms += solver.timer_stop()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    gpu_launches = solver.launch_count() - launches0
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        lt = torch.tensor([gpu_launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        gpu_launches = int(lt.item())
+    ms_per_step = total_ms / args.steps
+    value = n_points_total * sc.sub_steps * args.steps / (total_ms * 1e-3)
+
+    # ---- warm-L2 figure (same steps back to back, one event pair) for context
+    del solver
+    solver = fresh_solver()
+    barrier()
+    solver.timer_start()
+    solver.update(sc.dt, n=args.steps)
+    warm_ms = solver.timer_stop()
+    if dist is not None:
+        t = torch.tensor([warm_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        warm_ms = float(t.item())
+    value_warm = n_points_total * sc.sub_steps * args.steps / (warm_ms * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, every step (pinned memory, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        del solver
+        solver = fresh_solver()
+        n_local = solver.get_particle_len()
+        h_pos = torch.empty((n_local, 2), dtype=torch.float32).pin_memory()
+        h_prev = torch.empty((n_local, 2), dtype=torch.float32).pin_memory()
+        np_pos, np_prev = h_pos.numpy(), h_prev.numpy()
+        solver.read_particles(out_pos=np_pos, out_prev=np_prev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            solver.write_particles(np_pos, np_prev)          # H2D of the step's inputs
+            solver.update(sc.dt)                             # 8 substeps
+            solver.read_particles(out_pos=np_pos, out_prev=np_prev)  # D2H of the result (synchronises)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+            nb = torch.tensor([n_local], device="cuda", dtype=torch.int64)
+            dist.all_reduce(nb)
+            n_bytes = int(nb.item()) * 16
+        else:
+            n_bytes = n_local * 16
+        e2e = {"value": n_points_total * sc.sub_steps * args.steps / e2e_s, "unit": "particle-substeps/s",
+               "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": n_bytes, "ms_per_step": e2e_s / args.steps * 1e3,
+               "api": "bendy_write_particles + bendy_update + bendy_read_particles (pinned host buffers)"}
+
+    # ---- per-kernel event timing (eager launches with event pairs) -> roofline of the dominant kernel
+    del solver
+    solver = fresh_solver()
+    solver.set_profiling(True)
+    solver.kernel_times(reset=True)
+    prof_steps = max(2, min(args.steps, 25))
+    for _ in range(prof_steps):
+        flush_l2()
+        solver.update(sc.dt)
+    kt = solver.kernel_times(reset=True)
+    solver.set_profiling(False)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    n_sub = prof_steps * sc.sub_steps
+    grid = solver.grid() if sc.particle_radius > 0 else None
+    shard = solver.local_scene() if world > 1 else sc
+    alg = shard.algorithmic_bytes(grid)
+    class_bytes = {"integrate": alg["K1_integrate"], "links_local": alg["K3_links"], "links_global": 0,
+                   "grid_build": alg["K2_grid"], "narrowphase": alg["K2_narrow"], "poly_contact": alg["K4_polygon"],
+                   "fused": alg["K1_integrate"] + alg["K3_links"]}
+    kernels = {}
+    total_k_ms = sum(v["ms"] for v in kt.values())
+    for k, v in kt.items():
+        if v["launches"]:
+            per_sub = v["ms"] / n_sub
+            kernels[k] = {"ms_per_substep": per_sub, "launches_per_substep": v["launches"] / n_sub,
+                          "share": v["ms"] / total_k_ms if total_k_ms else 0.0}
+            if class_bytes.get(k):
+                kernels[k]["alg_GBps"] = class_bytes[k] / (per_sub * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    dom = max((k for k in kernels if class_bytes.get(k)), key=lambda k: kernels[k]["ms_per_substep"])
+    d = kernels[dom]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": d["alg_GBps"], "peak": peak, "unit": "GB/s",
+                "frac": d["alg_GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": d["ms_per_substep"] / max(d["launches_per_substep"], 1e-9),
+                "alg_bytes_per_substep_kernel": class_bytes[dom],
+                "substep": {"alg_bytes": alg["total"], "achieved": alg["total"] * sc.sub_steps / (ms_per_step * 1e-3) / 1e9,
+                            "frac": alg["total"] * sc.sub_steps / (ms_per_step * 1e-3) / 1e9 / peak,
+                            "achieved_warm_l2": alg["total"] * sc.sub_steps * args.steps / (warm_ms * 1e-3) / 1e9},
+                "kernels": kernels}
+    ncu_traffic = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(ncu_traffic):
+        try:
+            roofline["traffic"] = json.load(open(ncu_traffic)).get(dom)
+        except Exception:
+            pass
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        csc, what = cpu_baseline_sample(workload)
+        t0 = time.perf_counter()
+        v, _ = time_oracle(csc, 3, 1)
+        cpu = {"value": v, "unit": "particle-substeps/s", "cores": 1, "kind": "port", "sample": what + ", 3 steps",
+               "host_cores_available": os.cpu_count(), "seconds": time.perf_counter() - t0}
+
+    line = {
+        "metric": "particle-substeps/s", "value": value, "unit": "particle-substeps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": sc.name, "points": n_points_total, "particles": sc.n_particles, "links": sc.n_links,
+                   "circles": len(sc.circles_r), "polygons": len(sc.polygons), "substeps_per_step": sc.sub_steps,
+                   "substep_dt": 1.0 / 120.0 if workload != "c1" else 1.0 / 480.0,
+                   "l2": "warm between steps" if args.no_flush else "flushed between steps (256 MiB memset)",
+                   "parallelism": f"strips{world}" if world > 1 else "single"},
+        "value_warm_l2": value_warm, "wall_s_timed_region": wall,
+        "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "schedule": info,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

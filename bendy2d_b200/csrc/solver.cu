@@ -69,6 +69,8 @@ struct PendingEvent {
 struct bendy_solver {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};  // graph branches: circles, polygons
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     std::string err;
     int sticky = BENDY_OK;
 
@@ -110,9 +112,10 @@ struct bendy_solver {
     bool accel_pending = false;
     bool has_k = false;
     // grid
-    DevBuf<uint32_t> d_cell_of, d_cell_count, d_cell_start, d_tile_sum, d_slot_id, d_sorted_id;
+    DevBuf<uint32_t> d_cell_count, d_cell_start, d_tile_sum, d_sorted_id;
     DevBuf<float2> d_sorted_pos;
-    DevBuf<uint32_t> d_circ_tiles;
+    DevBuf<uint32_t> d_circ_tile_count, d_circ_tile_ids;
+    uint32_t n_scan_tiles = 0, n_circ_tiles = 0;
     DevBuf<unsigned long long> d_circ_acc;
     uint32_t n_cells = 0;
     // polygons
@@ -440,8 +443,6 @@ int Ops::rebuild() {
     }
     // grid buffers that depend only on the particle count
     if (s->nP) {
-        CK(s->d_cell_of.ensure(s->nP));
-        CK(s->d_slot_id.ensure(s->nP));
         CK(s->d_sorted_id.ensure(s->nP));
         CK(s->d_sorted_pos.ensure(s->nP));
     }
@@ -465,11 +466,17 @@ int Ops::ensure_ready() {
 
 // broadphase grid for these bounds: origin = bounds.pos, h >= 2*r_p, cell count bounded
 int Ops::grid_for(float bx, float by, float bw, float bh, StepParams *p, uint32_t *ncells) {
-    float h = s->grid_cell > 0.f ? s->grid_cell : 2.0f * s->particle_radius;
+    double wx = std::isfinite(bw) && bw > 0.f ? bw : 1.0, wy = std::isfinite(bh) && bh > 0.f ? bh : 1.0;
+    float h = s->grid_cell;
+    if (!(h > 0.f)) {
+        // auto: about two cells per particle (the per-cell scan traffic then stays below the per-disc
+        // traffic), never below the contact distance 2*r_p
+        double np = std::max<double>(s->p_pos.size(), 1.0);
+        h = (float)std::sqrt(wx * wy / (2.0 * np));
+    }
     if (h < 2.0f * s->particle_radius) h = 2.0f * s->particle_radius;
     if (!(h > 0.f)) h = 1.0f;
     const double max_cells = 67108864.0;  // 2^26
-    double wx = std::isfinite(bw) && bw > 0.f ? bw : 1.0, wy = std::isfinite(bh) && bh > 0.f ? bh : 1.0;
     while (std::ceil(wx / h) * std::ceil(wy / h) > max_cells) h *= 1.25f;
     int nx = (int)std::ceil(wx / h), ny = (int)std::ceil(wy / h);
     nx = std::max(nx, 1), ny = std::max(ny, 1);
@@ -518,11 +525,20 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
         drop_graph();
         if (discs) {
             s->n_cells = ncells;
-            CK(s->d_cell_count.ensure(ncells));
-            CK(cudaMemsetAsync(s->d_cell_count.p, 0, (size_t)ncells * sizeof(uint32_t), s->stream));
-            CK(s->d_cell_start.ensure(ncells));
-            CK(s->d_tile_sum.ensure(cdiv(ncells, SCAN_TILE) + 1));
-            if (s->nC) CK(s->d_circ_tiles.ensure((size_t)p.tnx * p.tny * (BENDY_CIRC_CAP + 1)));
+            // n_cells + 1 counters (the extra cell collects non-finite points), padded to whole scan tiles
+            s->n_scan_tiles = cdiv(ncells + 1, SCAN_TILE);
+            size_t padded = (size_t)s->n_scan_tiles * SCAN_TILE;
+            CK(s->d_cell_count.ensure(padded));
+            CK(cudaMemsetAsync(s->d_cell_count.p, 0, padded * sizeof(uint32_t), s->stream));
+            CK(s->d_cell_start.ensure(padded));
+            CK(s->d_tile_sum.ensure(s->n_scan_tiles));
+            CK(cudaMemsetAsync(s->d_tile_sum.p, 0, (size_t)s->n_scan_tiles * sizeof(uint32_t), s->stream));
+            if (s->nC) {
+                s->n_circ_tiles = (uint32_t)p.tnx * (uint32_t)p.tny;
+                CK(s->d_circ_tile_count.ensure(s->n_circ_tiles));
+                CK(cudaMemsetAsync(s->d_circ_tile_count.p, 0, (size_t)s->n_circ_tiles * sizeof(uint32_t), s->stream));
+                CK(s->d_circ_tile_ids.ensure((size_t)s->n_circ_tiles * BENDY_CIRC_CAP));
+            }
         }
         if (contact) {
             s->n_poly_tiles = ptiles;
@@ -546,7 +562,11 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
         if (_rc) return _rc;                                     \
     } while (0)
 
-// one substep, reference order (solver.rs:109-115)
+// one substep, reference order (solver.rs:109-115):
+//   gravity (fused into integrate) -> links -> dynamic collisions -> bounds -> integrate.
+// Free particles, circles and polygon points are disjoint worlds until the collision phase
+// (solver.rs:143-153), so while capturing a graph the circle and polygon chains run as parallel
+// branches beside the particle chain; eager (profiling) launches are simply serial.
 int Ops::launch_substep() {
     cudaStream_t st = s->stream;
     const StepParams *prm = s->d_prm.p;
@@ -555,116 +575,156 @@ int Ops::launch_substep() {
     const uint32_t nPoly = (uint32_t)s->polys.size();
     const bool contact = s->polygon_contact && nPoly && s->nP;
     const bool discs = s->particle_radius > 0.f && s->nP;
+    const bool branch = s->capturing;
+    const float *dk = K ? s->d_k.p : nullptr;
 
-    // -- polygon centres (Polygon::solve_links calls calc_center first: polygon.rs:219) + bins
-    if (nPoly) {
-        PolyArgs pa{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_static.p, nPoly, s->d_poly_center.p,
-                    s->d_poly_box.p,     s->d_poly_tiles.p, s->d_flags.p};
-        if (contact) {
-            // zero the tile counters (count word of every tile)
-            LAUNCH(BENDY_K_POLY_PREP, cudaMemsetAsync(s->d_poly_tiles.p, 0,
-                                                      (size_t)s->n_poly_tiles * (BENDY_POLY_CAP + 1) * sizeof(uint32_t), st));
-        }
-        LAUNCH(BENDY_K_POLY_PREP, k4_poly_prep<<<cdiv(nPoly, 128), 128, 0, st>>>(pa, prm, contact ? 1 : 0));
-    }
-    // -- apply_links (solver.rs:143-153): particle links, circle links, polygon links
     auto run_plan = [&](const LinkPlan &P, uint32_t base, const uint32_t *d_ps, const uint32_t *d_cs,
-                        const LocalLink *d_l, const GlobalLink *d_g) -> int {
+                        const LocalLink *d_l, const GlobalLink *d_g, cudaStream_t q, bool fuse_count) -> int {
         if (P.n_parts() && !P.local_links.empty()) {
             uint32_t maxp = 0;
             for (uint32_t p = 0; p < P.n_parts(); p++) maxp = std::max(maxp, P.part_start[p + 1] - P.part_start[p]);
             size_t smem = (size_t)maxp * (K ? 12 : 8);
-            if (K)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true><<<P.n_parts(), 256, smem, st>>>(
-                                                pos, s->d_k.p, base, d_ps, d_cs, d_l, P.n_local_colours));
+            K3CountArgs ca{prm, s->n_cells, s->d_cell_count.p, s->d_tile_sum.p};
+            const uint32_t np = P.n_parts(), C = P.n_local_colours;
+            if (K && fuse_count)
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, true><<<np, 128, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+            else if (K)
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, false><<<np, 128, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+            else if (fuse_count)
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true><<<np, 128, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
             else
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false><<<P.n_parts(), 256, smem, st>>>(
-                                                pos, nullptr, base, d_ps, d_cs, d_l, P.n_local_colours));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, false><<<np, 128, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
         }
         for (uint32_t c = 0; c < P.n_global_colours(); c++) {
             uint32_t l0 = P.gcolour_start[c], l1 = P.gcolour_start[c + 1];
             if (l0 == l1) continue;
             if (K)
-                LAUNCH(BENDY_K_LINKS_GLOBAL,
-                       k3_links_global<true><<<cdiv(l1 - l0, 256), 256, 0, st>>>(pos, s->d_k.p, base, d_g, l0, l1));
+                LAUNCH(BENDY_K_LINKS_GLOBAL, k3_links_global<true><<<cdiv(l1 - l0, 256), 256, 0, q>>>(pos, dk, base, d_g, l0, l1));
             else
-                LAUNCH(BENDY_K_LINKS_GLOBAL,
-                       k3_links_global<false><<<cdiv(l1 - l0, 256), 256, 0, st>>>(pos, nullptr, base, d_g, l0, l1));
+                LAUNCH(BENDY_K_LINKS_GLOBAL, k3_links_global<false><<<cdiv(l1 - l0, 256), 256, 0, q>>>(pos, dk, base, d_g, l0, l1));
         }
         return BENDY_OK;
     };
-    if (int rc = run_plan(s->plan_p, 0, s->d_part_start.p, s->d_part_cs.p, s->d_local.p, s->d_global.p)) return rc;
+
+    const bool circ_work = !s->cl.empty() || s->nC >= 2 || (discs && s->nC);
+    const bool poly_work = nPoly > 0;
+    cudaStream_t qc = st, qg = st;
+    if (branch && (circ_work || poly_work)) {
+        CK(cudaEventRecord(s->ev_fork, st));
+        if (circ_work) {
+            qc = s->side[0];
+            CK(cudaStreamWaitEvent(qc, s->ev_fork, 0));
+        }
+        if (poly_work) {
+            qg = s->side[1];
+            CK(cudaStreamWaitEvent(qg, s->ev_fork, 0));
+        }
+    }
+
+    // ---- polygon chain: centre (polygon.rs:219) -> own links (polygon.rs:220-222) -> AABB + obstacle bins
+    PolyArgs pa{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_static.p, nPoly, s->d_poly_center.p,
+                s->d_poly_box.p,     s->d_poly_tiles.p, s->d_flags.p};
+    if (poly_work) {
+        LAUNCH(BENDY_K_POLY_PREP, k4_poly_center<<<cdiv(nPoly, 128), 128, 0, qg>>>(pa));
+        if (int rc = run_plan(s->plan_g, s->nP + s->nC, s->d_gpart_start.p, s->d_gpart_cs.p, s->d_glocal.p,
+                              s->d_gglobal.p, qg, false))
+            return rc;
+        if (contact) {
+            LAUNCH(BENDY_K_POLY_PREP, cudaMemsetAsync(s->d_poly_tiles.p, 0,
+                                                      (size_t)s->n_poly_tiles * (BENDY_POLY_CAP + 1) * sizeof(uint32_t), qg));
+            LAUNCH(BENDY_K_POLY_PREP, k4_poly_box_bin<<<cdiv(nPoly, 128), 128, 0, qg>>>(pa, prm));
+        }
+    }
+    // ---- circle chain: circle links (solver.rs:147-149) -> circle-circle pass (solver.rs:168-177) -> bins
     if (!s->cl.empty())
         LAUNCH(BENDY_K_LINKS_CIRCLE,
-               k3_circle_links<<<1, 32, 0, st>>>(pos + s->nP, s->d_crad.p, s->d_clinks.p, (uint32_t)s->cl.size()));
-    if (int rc = run_plan(s->plan_g, s->nP + s->nC, s->d_gpart_start.p, s->d_gpart_cs.p, s->d_glocal.p,
-                          s->d_gglobal.p))
-        return rc;
-
-    // -- solve_dynamic_collisions (solver.rs:167-188)
+               k3_circle_links<<<1, 32, 0, qc>>>(pos + s->nP, s->d_crad.p, s->d_clinks.p, (uint32_t)s->cl.size()));
     if (s->nC >= 2) {
         size_t smem = s->nC <= 4096 ? (size_t)s->nC * 12 : 0;
-        LAUNCH(BENDY_K_CIRCLES, k_circles_exact<<<1, 1024, smem, st>>>(pos + s->nP, s->d_crad.p, s->nC, smem ? 1 : 0));
+        LAUNCH(BENDY_K_CIRCLES, k_circles_exact<<<1, 1024, smem, qc>>>(pos + s->nP, s->d_crad.p, s->nC, smem ? 1 : 0));
     }
+    if (discs && s->nC)
+        LAUNCH(BENDY_K_CIRCLES, k2_circle_bin<<<cdiv(s->nC, 128), 128, 0, qc>>>(pos + s->nP, s->d_crad.p, s->nC, prm,
+                                                                                 s->d_circ_tile_count.p, s->d_circ_tile_ids.p));
+
+    // ---- particle chain: links (solver.rs:144-146) [+ histogram] -> scan -> scatter
+    const uint32_t n_in_parts = s->plan_p.n_parts() ? s->plan_p.part_start.back() : 0u;
+    const bool fuse_count = discs && s->plan_p.n_global_colours() == 0 && n_in_parts > 0;
+    if (int rc = run_plan(s->plan_p, 0, s->d_part_start.p, s->d_part_cs.p, s->d_local.p, s->d_global.p, st, fuse_count))
+        return rc;
     if (discs) {
-        const uint32_t n_tiles = cdiv(s->n_cells, SCAN_TILE);
+        const uint32_t c0 = fuse_count ? n_in_parts : 0u;
+        if (c0 < s->nP)
+            LAUNCH(BENDY_K_GRID_BUILD, k2_count<<<cdiv(s->nP - c0, 256), 256, 0, st>>>(pos, c0, s->nP, prm, s->n_cells,
+                                                                                       s->d_cell_count.p, s->d_tile_sum.p));
         LAUNCH(BENDY_K_GRID_BUILD,
-               k2_hash_count<<<cdiv(s->nP, 256), 256, 0, st>>>(pos, s->nP, prm, s->d_cell_of.p, s->d_cell_count.p));
+               k2_scan<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p));
         LAUNCH(BENDY_K_GRID_BUILD,
-               k2_scan_a<<<n_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->n_cells, s->d_tile_sum.p));
-        LAUNCH(BENDY_K_GRID_BUILD, k2_scan_b<<<1, SCAN_THREADS, 0, st>>>(s->d_tile_sum.p, n_tiles));
-        LAUNCH(BENDY_K_GRID_BUILD, k2_scan_c<<<n_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->n_cells,
-                                                                                s->d_tile_sum.p, s->d_cell_start.p));
-        LAUNCH(BENDY_K_GRID_BUILD,
-               k2_scatter<<<cdiv(s->nP, 256), 256, 0, st>>>(s->d_cell_of.p, s->nP, s->d_cell_start.p, s->d_slot_id.p));
-        LAUNCH(BENDY_K_GRID_BUILD,
-               k2_canon<<<cdiv(s->nP, 256), 256, 0, st>>>(s->d_slot_id.p, s->d_cell_of.p, s->d_cell_start.p, s->n_cells,
-                                                          pos, s->d_sorted_id.p, s->d_sorted_pos.p));
-        if (s->nC)
-            LAUNCH(BENDY_K_CIRCLES, k2_circle_bin<<<cdiv((uint32_t)(s->prm.tnx * s->prm.tny), 128), 128, 0, st>>>(
-                                        pos + s->nP, s->d_crad.p, s->nC, prm, s->d_circ_tiles.p));
-        K2Args a{pos,        K ? s->d_k.p : nullptr, s->d_sorted_id.p, s->d_sorted_pos.p,
-                 s->d_cell_start.p, s->n_cells,      s->nP,            s->nC,
-                 s->d_crad.p,       s->nC ? s->d_circ_tiles.p : nullptr, s->d_circ_acc.p};
-        if (K)
-            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow<true><<<cdiv(s->nP, 128), 128, 0, st>>>(a, prm));
-        else
-            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow<false><<<cdiv(s->nP, 128), 128, 0, st>>>(a, prm));
-        if (s->nC)
-            LAUNCH(BENDY_K_CIRCLES, k2_circle_apply<<<cdiv(s->nC, 128), 128, 0, st>>>(pos + s->nP, s->d_circ_acc.p, s->nC));
+               k2_scatter<<<cdiv(s->nP, 256), 256, 0, st>>>(pos, s->nP, prm, s->n_cells, s->d_cell_start.p, s->d_tile_sum.p,
+                                                            s->n_scan_tiles, s->d_sorted_pos.p, s->d_sorted_id.p));
     }
-    if (contact) {
-        K4Args a{pos,
-                 K ? s->d_k.p : nullptr,
-                 s->nP,
-                 pos + s->nP + s->nC,
-                 s->d_poly_start.p,
-                 s->d_poly_center.p,
-                 s->d_poly_box.p,
-                 s->d_poly_tiles.p};
-        if (K)
-            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<true><<<cdiv(s->nP, 128), 128, 0, st>>>(a, prm));
-        else
-            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<false><<<cdiv(s->nP, 128), 128, 0, st>>>(a, prm));
+    // ---- join: the collision phase needs all three worlds
+    if (branch) {
+        if (qc != st) {
+            CK(cudaEventRecord(s->ev_join[0], qc));
+            CK(cudaStreamWaitEvent(st, s->ev_join[0], 0));
+        }
+        if (qg != st) {
+            CK(cudaEventRecord(s->ev_join[1], qg));
+            CK(cudaStreamWaitEvent(st, s->ev_join[1], 0));
+        }
     }
-    // -- solve_boundary_collisions + update_positions (solver.rs:113-114), gravity fused
-    {
-        K1Args a{pos,         s->d_prev.p,       s->accel_pending ? s->d_accel.p : nullptr, K ? s->d_k.p : nullptr,
-                 s->d_crad.p, s->d_gstatic.p, s->nP, s->nC, s->N};
+    K4Args k4{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_center.p, s->d_poly_box.p, s->d_poly_tiles.p};
+    K1Args k1{pos,         s->d_prev.p,    s->accel_pending ? s->d_accel.p : nullptr, dk,
+              s->d_crad.p, s->d_gstatic.p, s->nP, s->nC, s->N};
+    uint32_t k1_first = 0;  // first point still to be integrated by K1
+    if (discs) {
+        // narrowphase + polygon contact + bounds + integrate for the free particles, fused
+        K2Args a{pos,     s->d_prev.p,   dk,    s->d_sorted_id.p,        s->d_sorted_pos.p,       s->d_cell_start.p, s->n_cells,
+                 s->nP,   s->nP,         s->nC, s->d_crad.p,             s->d_circ_tile_count.p,  s->d_circ_tile_ids.p,
+                 s->d_circ_acc.p};
+        const uint32_t blocks = cdiv(s->nP, 128);
+        if (K && contact)
+            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<true, true><<<blocks, 128, 0, st>>>(a, k4, prm));
+        else if (K)
+            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<true, false><<<blocks, 128, 0, st>>>(a, k4, prm));
+        else if (contact)
+            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<false, true><<<blocks, 128, 0, st>>>(a, k4, prm));
+        else
+            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<false, false><<<blocks, 128, 0, st>>>(a, k4, prm));
+        if (s->nC)
+            LAUNCH(BENDY_K_CIRCLES, k2_circle_apply<<<cdiv(s->nC, 128), 128, 0, st>>>(pos + s->nP, s->d_circ_acc.p, s->nC,
+                                                                                       s->d_circ_tile_count.p, s->n_circ_tiles));
+        k1_first = s->nP;
+    } else if (contact) {
+        if (K)
+            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<true><<<cdiv(s->nP, 128), 128, 0, st>>>(pos, dk, s->nP, k4, prm));
+        else
+            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<false><<<cdiv(s->nP, 128), 128, 0, st>>>(pos, dk, s->nP, k4, prm));
+    }
+    // ---- solve_boundary_collisions + update_positions (solver.rs:113-114), gravity fused
+    if (k1_first == 0) {
         uint32_t blocks = cdiv(s->Npad / 2, 256);
         if (blocks) {
-            if (s->accel_pending) {
-                if (K)
-                    LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, true><<<blocks, 256, 0, st>>>(a, prm));
-                else
-                    LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, false><<<blocks, 256, 0, st>>>(a, prm));
-            } else {
-                if (K)
-                    LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, true><<<blocks, 256, 0, st>>>(a, prm));
-                else
-                    LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, false><<<blocks, 256, 0, st>>>(a, prm));
-            }
+            if (s->accel_pending && K)
+                LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, true><<<blocks, 256, 0, st>>>(k1, prm));
+            else if (s->accel_pending)
+                LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, false><<<blocks, 256, 0, st>>>(k1, prm));
+            else if (K)
+                LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, true><<<blocks, 256, 0, st>>>(k1, prm));
+            else
+                LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, false><<<blocks, 256, 0, st>>>(k1, prm));
         }
+    } else if (s->N > k1_first) {
+        const uint32_t n = s->N - k1_first, blocks = cdiv(n, 256);
+        if (s->accel_pending && K)
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, true><<<blocks, 256, 0, st>>>(k1, k1_first, n, prm));
+        else if (s->accel_pending)
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, false><<<blocks, 256, 0, st>>>(k1, k1_first, n, prm));
+        else if (K)
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, true><<<blocks, 256, 0, st>>>(k1, k1_first, n, prm));
+        else
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, false><<<blocks, 256, 0, st>>>(k1, k1_first, n, prm));
     }
     return BENDY_OK;
 }
@@ -740,6 +800,10 @@ bendy_solver::~bendy_solver() {
             if (prm_ring_ev[i]) cudaEventDestroy(prm_ring_ev[i]);
         cudaFreeHost(h_prm_ring);
     }
+    for (cudaEvent_t e : {ev_fork, ev_join[0], ev_join[1]})
+        if (e) cudaEventDestroy(e);
+    for (cudaStream_t q : side)
+        if (q) cudaStreamDestroy(q);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -785,6 +849,11 @@ bendy_solver *bendy_create(int device) {
     s->device = device;
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&s->side[0], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&s->side[1], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&s->ev_join[0], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&s->ev_join[1], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&s->t0)) != cudaSuccess || (e = cudaEventCreate(&s->t1)) != cudaSuccess) {
         g_last_error = std::string("CUDA init failed: ") + cudaGetErrorString(e);
         return nullptr;

@@ -89,12 +89,11 @@ class Scene:
         k4 = self.polygon_contact and len(self.polygons) > 0
         out = {
             "K1_integrate": n_pts * 32,
-            "K2_grid": n_disc * 24 + self.n_cells(grid) * 16,  # hash R8 W4 | scatter R4+8 W8 ...
-            "K2_narrow": n_disc * 32,
+            "K2_grid": n_disc * 36 + self.n_cells(grid) * 16,  # hash R8 W4 | scatter R4+8 W8+4 | cells 16
+            "K2_narrow": n_disc * 20,                          # narrowphase R8+4 W8
             "K3_links": (self.n_links + n_poly_links) * 44,
             "K4_polygon": (self.n_particles * 16 + self.n_polygon_points * 8 + len(self.polygons) * 24) if k4 else 0,
         }
-        # SURVEY: N_disc*56 total for K2 = 24 (hash+scatter) + 32 (gather/sort copy + narrowphase)
         out["total"] = sum(out.values())
         return out
 

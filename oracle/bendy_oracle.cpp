@@ -357,11 +357,11 @@ static inline int cell_coord(float x, float o, float inv_h, int n) {
 // ext — PARITY UNPINNED BY THE REFERENCE (free particles collide with nothing there,
 // solver.rs:167-188).  Spec: every free particle is a disc of radius r_p; the
 // per-pair rule is Circle::solve_circle (circle.rs:32-45) seen from the disc being updated;
-// update discipline is Jacobi: all overlap tests and normals use the positions at phase entry,
-// a disc adds its corrections in the canonical order (3x3 cells row-major dy,dx; ascending rank
-// inside a cell; then Circles by ascending index).  A Circle's correction from particles is
-// accumulated in 2^-40 fixed point (order independent).  For a contact graph that is a matching
-// this equals the reference's sequential pass bit-for-bit.
+// update discipline is Jacobi: all overlap tests and normals use the positions at phase entry.
+// Each per-pair correction (an f32 computed exactly like circle.rs:42) is converted to 2^-40 fixed
+// point and summed in int64, so the sum does not depend on the visiting order; the disc then moves
+// by pos + (float)sum.  A correction >= 2^-17 converts exactly, so for a contact graph that is a
+// matching this equals the reference's sequential pass bit-for-bit.  The grid only prunes pairs.
 static void ext_disc_contacts(bo_world &w) {
     const size_t n = w.particles.size();
     const size_t nc = w.circles.size();
@@ -372,19 +372,22 @@ static void ext_disc_contacts(bo_world &w) {
     for (size_t c = 0; c < nc; c++) QC[c] = w.circles[c].point.pos;
 
     const int nx = w.grid_nx, ny = w.grid_ny;
-    std::vector<uint64_t> key(n);  // (cell << 32) | rank, sorted
     std::vector<uint32_t> cell(n);
+    const uint32_t NOCELL = 0xFFFFFFFFu;  // non-finite positions overlap nothing (all compares false)
     for (size_t i = 0; i < n; i++) {
+        if (!std::isfinite(Q[i].x) || !std::isfinite(Q[i].y)) {
+            cell[i] = NOCELL;
+            continue;
+        }
         int cx = cell_coord(Q[i].x, w.grid_ox, w.grid_inv_h, nx);
         int cy = cell_coord(Q[i].y, w.grid_oy, w.grid_inv_h, ny);
         cell[i] = (uint32_t)cy * (uint32_t)nx + (uint32_t)cx;
     }
     std::vector<uint32_t> order(n);
     for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
-    auto rank_of = [&](uint32_t i) { return w.point_rank.empty() ? i : w.point_rank[i]; };
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
         if (cell[a] != cell[b]) return cell[a] < cell[b];
-        return rank_of(a) < rank_of(b);
+        return a < b;
     });
     std::vector<uint32_t> sorted_cell(n);
     for (size_t s = 0; s < n; s++) sorted_cell[s] = cell[order[s]];
@@ -396,8 +399,11 @@ static void ext_disc_contacts(bo_world &w) {
     const float rp_sq = rp * rp;
     std::vector<V2> out(n);
     for (size_t i = 0; i < n; i++) {
-        V2 p = Q[i];
+        out[i] = Q[i];
+        if (cell[i] == NOCELL) continue;
         const float ki = pk(w, i);
+        int64_t sx = 0, sy = 0;
+        bool moved = false;
         int cx = (int)(cell[i] % (uint32_t)nx), cy = (int)(cell[i] / (uint32_t)nx);
         for (int dy = -1; dy <= 1; dy++) {
             int yy = cy + dy;
@@ -418,7 +424,9 @@ static void ext_disc_contacts(bo_world &w) {
                     float overlap = radius_sum - std::sqrt(dist_sqr);
                     float wi = ki * rp_sq, wj = kj * rp_sq;  // k_i*r_j^2, k_j*r_i^2
                     float scale = 1.0f / (wj + wi);
-                    p = p + normal * scale * overlap * wi;
+                    V2 c = normal * scale * overlap * wi;
+                    sx += to_fix(c.x), sy += to_fix(c.y);
+                    moved = true;
                 }
             }
         }
@@ -435,13 +443,15 @@ static void ext_disc_contacts(bo_world &w) {
                 float wi = ki * (R * R), wc = kc * rp_sq;
                 float scale = 1.0f / (wc + wi);
                 V2 x = normal * scale * overlap;
-                p = p + x * wi;
+                V2 ci = x * wi;
+                sx += to_fix(ci.x), sy += to_fix(ci.y);
+                moved = true;
                 V2 cc = x * wc;
                 accx[c] += to_fix(-cc.x);
                 accy[c] += to_fix(-cc.y);
             }
         }
-        out[i] = p;
+        if (moved) out[i] = v2(Q[i].x + from_fix(sx), Q[i].y + from_fix(sy));
     }
     for (size_t i = 0; i < n; i++) w.particles[i].pos = out[i];
     for (size_t c = 0; c < nc; c++) {
@@ -612,6 +622,14 @@ void bo_set_bounds(bo_world *w, float bx, float by, float sx, float sy) {
 }
 
 void bo_add_particle(bo_world *w, float x, float y) { w->particles.push_back(particle_new(v2(x, y))); }
+void bo_add_particles(bo_world *w, const float *pos_xy, size_t n) {
+    w->particles.reserve(w->particles.size() + n);
+    for (size_t i = 0; i < n; i++) w->particles.push_back(particle_new(v2(pos_xy[2 * i], pos_xy[2 * i + 1])));
+}
+void bo_add_particle_links(bo_world *w, const uint32_t *ab, const float *len, size_t n) {
+    w->particle_links.reserve(w->particle_links.size() + n);
+    for (size_t k = 0; k < n; k++) w->particle_links.push_back(Link{ab[2 * k], ab[2 * k + 1], len[k]});
+}
 void bo_add_circle(bo_world *w, float px, float py, float qx, float qy, float ax, float ay, float radius) {
     w->circles.push_back(Circle{Particle{v2(px, py), v2(qx, qy), v2(ax, ay)}, radius});
 }

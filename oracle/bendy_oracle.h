@@ -44,6 +44,8 @@ void bo_set_bounds(bo_world *w, float bx, float by, float sx, float sy);
 
 /* ---- scene construction, solver.rs:52-67 ---- */
 void bo_add_particle(bo_world *w, float x, float y); /* Particle::new: prev=pos, acc=0 */
+void bo_add_particles(bo_world *w, const float *pos_xy, size_t n);                       /* bulk form */
+void bo_add_particle_links(bo_world *w, const uint32_t *ab, const float *len, size_t n); /* bulk form */
 void bo_add_circle(bo_world *w, float px, float py, float qx, float qy, float ax, float ay, float radius);
 int bo_add_polygon(bo_world *w, const float *pos_xy, const float *prev_xy, const float *acc_xy, size_t nv,
                    const uint32_t *link_ab, const float *link_len, size_t nl, int is_static, float cx,

@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
         "bo_set_gravity": (None, [vp, fl, fl]),
         "bo_set_bounds": (None, [vp, fl, fl, fl, fl]),
         "bo_add_particle": (None, [vp, fl, fl]),
+        "bo_add_particles": (None, [vp, f32p, sz]),
+        "bo_add_particle_links": (None, [vp, u32p, f32p, sz]),
         "bo_add_circle": (None, [vp, fl, fl, fl, fl, fl, fl, fl]),
         "bo_add_polygon": (C.c_int, [vp, f32p, f32p, f32p, sz, u32p, f32p, sz, C.c_int, fl, fl]),
         "bo_add_polygon_new": (C.c_int, [vp, f32p, sz, C.c_int]),
@@ -143,8 +145,7 @@ class OracleSolver:
 
     def add_particles(self, pos_xy):
         p = _f(pos_xy).reshape(-1, 2)
-        for x, y in p:
-            self._L.bo_add_particle(self._h, x, y)
+        self._L.bo_add_particles(self._h, _fp(p), len(p))
 
     def add_circle(self, pos, radius, prev=None, acc=(0.0, 0.0)):
         prev = pos if prev is None else prev
@@ -177,8 +178,7 @@ class OracleSolver:
     def add_particle_links(self, ab, lengths):
         ab = _u(ab).reshape(-1, 2)
         ln = _f(lengths).reshape(-1)
-        for (a, b), l in zip(ab, ln):
-            self._L.bo_add_particle_link(self._h, int(a), int(b), l)
+        self._L.bo_add_particle_links(self._h, _up(ab), _fp(ln), len(ln))
 
     def add_circle_link(self, a, b, length):
         self._L.bo_add_circle_link(self._h, a, b, length)

@@ -233,3 +233,31 @@ def test_schedule_order_replay_of_disjoint_links_is_identical():
     assert np.array_equal(bits(a.particles()[0]), bits(b.particles()[0]))
     with pytest.raises(ValueError):
         b.set_link_order([0, 0, 1, 2])
+
+
+def test_ext_disc_contact_equals_reference_pair_rule_on_a_matching():
+    """ext (unpinned) disc contact: for isolated pairs the Jacobi/fixed-point rule must reproduce
+    Circle::solve_circle (circle.rs:32-45) bit for bit."""
+    rng = np.random.default_rng(5)
+    n_pairs = 400
+    base = np.stack([10 + 4.0 * (np.arange(n_pairs) % 20), 10 + 4.0 * (np.arange(n_pairs) // 20)], 1)
+    ang = rng.uniform(0, 2 * np.pi, n_pairs)
+    sep = rng.uniform(0.02, 0.1999, n_pairs)
+    a = (base + 0.5 * sep[:, None] * np.stack([np.cos(ang), np.sin(ang)], 1)).astype(f32)
+    b = (base - 0.5 * sep[:, None] * np.stack([np.cos(ang), np.sin(ang)], 1)).astype(f32)
+    s = bo.OracleSolver()
+    s.set_gravity(0, 0)
+    s.set_bounds(0, 0, 100, 100)
+    pts = np.empty((2 * n_pairs, 2), f32)
+    pts[0::2], pts[1::2] = a, b
+    s.add_particles(pts)
+    s.set_particle_radius(0.1)
+    s.set_grid(0, 0, 1 / 0.2, 500, 500)
+    s.update(0.01)
+    _, prev = s.particles()  # prev = post-contact position (integrate copies pos into prev)
+    hits = 0
+    for k in range(n_pairs):
+        hit, p1, p2 = bo.prim_circle_solve(a[k], b[k], 0.1, 0.1)
+        hits += hit
+        assert np.array_equal(bits(prev[2 * k]), bits(p1)) and np.array_equal(bits(prev[2 * k + 1]), bits(p2)), k
+    assert hits > 300
