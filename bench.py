@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (not the headline)")
+    ap.add_argument("--grid-cell", type=float, default=0.0, help="override the broadphase cell edge (0 = auto)")
+    ap.add_argument("--pack-points", type=int, default=0, help="override the link-partition pack target")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -212,6 +214,10 @@ def main():
         else:
             sv = Solver(local)
             sc.load_into(sv)
+            if args.grid_cell > 0:
+                sv.set_grid_cell(args.grid_cell)
+            if args.pack_points > 0:
+                sv.set_plan_params(args.pack_points, 0)
         for _ in range(n_warm):
             sv.update(sc.dt)
         sv.synchronize()

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -112,7 +113,9 @@ struct bendy_solver {
     bool accel_pending = false;
     bool has_k = false;
     // grid
-    DevBuf<uint32_t> d_cell_count, d_cell_start, d_tile_sum, d_sorted_id;
+    DevBuf<uint32_t> d_cell_count, d_cell_start, d_tile_sum, d_sorted_id, d_slot_of;
+    uint32_t k3_threads = 128;  // BENDY_K3_THREADS
+    bool scatter_agg = false;   // BENDY_SCATTER_AGG
     DevBuf<float2> d_sorted_pos;
     DevBuf<uint32_t> d_circ_tile_count, d_circ_tile_ids;
     uint32_t n_scan_tiles = 0, n_circ_tiles = 0;
@@ -444,6 +447,7 @@ int Ops::rebuild() {
     // grid buffers that depend only on the particle count
     if (s->nP) {
         CK(s->d_sorted_id.ensure(s->nP));
+        CK(s->d_slot_of.ensure(s->nP));
         CK(s->d_sorted_pos.ensure(s->nP));
     }
     if (s->nC) {
@@ -584,16 +588,17 @@ int Ops::launch_substep() {
             uint32_t maxp = 0;
             for (uint32_t p = 0; p < P.n_parts(); p++) maxp = std::max(maxp, P.part_start[p + 1] - P.part_start[p]);
             size_t smem = (size_t)maxp * (K ? 12 : 8);
-            K3CountArgs ca{prm, s->n_cells, s->d_cell_count.p, s->d_tile_sum.p};
+            K3CountArgs ca{prm, s->n_cells, s->d_cell_count.p};
+            const uint32_t T = s->k3_threads;
             const uint32_t np = P.n_parts(), C = P.n_local_colours;
             if (K && fuse_count)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, true><<<np, 128, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, true><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
             else if (K)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, false><<<np, 128, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
             else if (fuse_count)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true><<<np, 128, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
             else
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, false><<<np, 128, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
         }
         for (uint32_t c = 0; c < P.n_global_colours(); c++) {
             uint32_t l0 = P.gcolour_start[c], l1 = P.gcolour_start[c + 1];
@@ -655,13 +660,25 @@ int Ops::launch_substep() {
     if (discs) {
         const uint32_t c0 = fuse_count ? n_in_parts : 0u;
         if (c0 < s->nP)
-            LAUNCH(BENDY_K_GRID_BUILD, k2_count<<<cdiv(s->nP - c0, 256), 256, 0, st>>>(pos, c0, s->nP, prm, s->n_cells,
-                                                                                       s->d_cell_count.p, s->d_tile_sum.p));
+            LAUNCH(BENDY_K_GRID_BUILD,
+                   k2_count<<<cdiv(s->nP - c0, 256), 256, 0, st>>>(pos, c0, s->nP, prm, s->n_cells, s->d_cell_count.p));
+        LAUNCH(BENDY_K_GRID_BUILD,
+               k2_tile_reduce<<<cdiv(s->n_scan_tiles, 8), 256, 0, st>>>(s->d_cell_count.p, s->n_scan_tiles, s->d_tile_sum.p));
         LAUNCH(BENDY_K_GRID_BUILD,
                k2_scan<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p));
-        LAUNCH(BENDY_K_GRID_BUILD,
-               k2_scatter<<<cdiv(s->nP, 256), 256, 0, st>>>(pos, s->nP, prm, s->n_cells, s->d_cell_start.p, s->d_tile_sum.p,
-                                                            s->n_scan_tiles, s->d_sorted_pos.p, s->d_sorted_id.p));
+#define SCATTER(ID, AG)                                                                                              \
+    LAUNCH(BENDY_K_GRID_BUILD, k2_scatter<ID, AG><<<cdiv(s->nP, 256), 256, 0, st>>>(                                  \
+                                   pos, s->nP, prm, s->n_cells, s->d_cell_start.p, s->d_sorted_pos.p, s->d_slot_of.p,  \
+                                   s->d_sorted_id.p))
+        if (K && s->scatter_agg)
+            SCATTER(true, true);
+        else if (K)
+            SCATTER(true, false);
+        else if (s->scatter_agg)
+            SCATTER(false, true);
+        else
+            SCATTER(false, false);
+#undef SCATTER
     }
     // ---- join: the collision phase needs all three worlds
     if (branch) {
@@ -680,7 +697,7 @@ int Ops::launch_substep() {
     uint32_t k1_first = 0;  // first point still to be integrated by K1
     if (discs) {
         // narrowphase + polygon contact + bounds + integrate for the free particles, fused
-        K2Args a{pos,     s->d_prev.p,   dk,    s->d_sorted_id.p,        s->d_sorted_pos.p,       s->d_cell_start.p, s->n_cells,
+        K2Args a{pos,     s->d_prev.p,   dk,    s->d_slot_of.p, s->d_sorted_id.p, s->d_sorted_pos.p, s->d_cell_start.p, s->n_cells,
                  s->nP,   s->nP,         s->nC, s->d_crad.p,             s->d_circ_tile_count.p,  s->d_circ_tile_ids.p,
                  s->d_circ_acc.p};
         const uint32_t blocks = cdiv(s->nP, 128);
@@ -847,6 +864,11 @@ bendy_solver *bendy_create(int device) {
     }
     std::unique_ptr<bendy_solver> s(new bendy_solver());
     s->device = device;
+    if (const char *v = getenv("BENDY_K3_THREADS")) {  // tuning knobs (not part of the ABI)
+        int t = atoi(v);
+        if (t >= 32 && t <= 1024 && t % 32 == 0) s->k3_threads = (uint32_t)t;
+    }
+    if (const char *v = getenv("BENDY_SCATTER_AGG")) s->scatter_agg = atoi(v) != 0;
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->side[0], cudaStreamNonBlocking)) != cudaSuccess ||
