@@ -71,7 +71,7 @@ struct bendy_solver {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};  // graph branches: circles, polygons
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_main = nullptr;
     std::string err;
     int sticky = BENDY_OK;
 
@@ -114,6 +114,8 @@ struct bendy_solver {
     bool has_k = false;
     // grid
     DevBuf<uint32_t> d_cell_count, d_cell_start, d_tile_sum, d_sorted_id, d_slot_of;
+    DevBuf<uint32_t> d_scan_barrier;
+    uint32_t scan_fused_capacity = 0;  // CTAs of k2_scan_fused that can be resident at once
     uint32_t k3_threads = 128;  // BENDY_K3_THREADS
     bool scatter_agg = false;   // BENDY_SCATTER_AGG
     DevBuf<float2> d_sorted_pos;
@@ -475,8 +477,9 @@ int Ops::grid_for(float bx, float by, float bw, float bh, StepParams *p, uint32_
     if (!(h > 0.f)) {
         // auto: about two cells per particle (the per-cell scan traffic then stays below the per-disc
         // traffic), never below the contact distance 2*r_p
+        // and, so that a disc's partners lie in a 2x2 block of cells, at least 4.2*r_p
         double np = std::max<double>(s->p_pos.size(), 1.0);
-        h = (float)std::sqrt(wx * wy / (2.0 * np));
+        h = std::max((float)std::sqrt(wx * wy / (2.0 * np)), 4.2f * s->particle_radius);
     }
     if (h < 2.0f * s->particle_radius) h = 2.0f * s->particle_radius;
     if (!(h > 0.f)) h = 1.0f;
@@ -486,6 +489,7 @@ int Ops::grid_for(float bx, float by, float bw, float bh, StepParams *p, uint32_
     nx = std::max(nx, 1), ny = std::max(ny, 1);
     p->gox = bx, p->goy = by, p->h = h, p->inv_h = 1.0f / h;
     p->nx = nx, p->ny = ny;
+    p->quad = h >= 4.2f * s->particle_radius ? 1 : 0;
     p->tnx = (nx + (1 << BENDY_TILE_SHIFT) - 1) >> BENDY_TILE_SHIFT;
     p->tny = (ny + (1 << BENDY_TILE_SHIFT) - 1) >> BENDY_TILE_SHIFT;
     *ncells = (uint32_t)nx * (uint32_t)ny;
@@ -506,7 +510,7 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
     if (discs) {
         grid_for(bx, by, bw, bh, &p, &ncells);
     } else {
-        p.nx = p.ny = p.tnx = p.tny = 1, p.gox = bx, p.goy = by, p.h = 1.f, p.inv_h = 1.f;
+        p.nx = p.ny = p.tnx = p.tny = 1, p.gox = bx, p.goy = by, p.h = 1.f, p.inv_h = 1.f, p.quad = 0;
     }
     const bool contact = s->polygon_contact && !s->polys.empty() && s->nP > 0;
     uint32_t ptiles = 0;
@@ -535,6 +539,16 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
             CK(s->d_cell_count.ensure(padded));
             CK(cudaMemsetAsync(s->d_cell_count.p, 0, padded * sizeof(uint32_t), s->stream));
             CK(s->d_cell_start.ensure(padded));
+            CK(s->d_scan_barrier.ensure(1));
+            CK(cudaMemsetAsync(s->d_scan_barrier.p, 0, sizeof(uint32_t), s->stream));
+            if (!s->scan_fused_capacity) {
+                int per_sm = 0, sms = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_fused, SCAN_THREADS, 0));
+                CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+                s->scan_fused_capacity = (uint32_t)std::max(per_sm * sms, 1);
+                if (const char *v = getenv("BENDY_SCAN_FUSED"))
+                    if (atoi(v) == 0) s->scan_fused_capacity = 1;
+            }
             CK(s->d_tile_sum.ensure(s->n_scan_tiles));
             CK(cudaMemsetAsync(s->d_tile_sum.p, 0, (size_t)s->n_scan_tiles * sizeof(uint32_t), s->stream));
             if (s->nC) {
@@ -611,20 +625,14 @@ int Ops::launch_substep() {
         return BENDY_OK;
     };
 
-    const bool circ_work = !s->cl.empty() || s->nC >= 2 || (discs && s->nC);
+    // While capturing, the side streams were forked from the main stream by build_graph(); the
+    // circle chain runs on side[0], the polygon chain on side[1].  Their tails (integrate) of
+    // substep k are queued behind the narrowphase of substep k and overlap the particle chain
+    // of substep k+1, which never touches circle or polygon state before ITS join.
+    const bool circ_work = s->nC > 0;
     const bool poly_work = nPoly > 0;
-    cudaStream_t qc = st, qg = st;
-    if (branch && (circ_work || poly_work)) {
-        CK(cudaEventRecord(s->ev_fork, st));
-        if (circ_work) {
-            qc = s->side[0];
-            CK(cudaStreamWaitEvent(qc, s->ev_fork, 0));
-        }
-        if (poly_work) {
-            qg = s->side[1];
-            CK(cudaStreamWaitEvent(qg, s->ev_fork, 0));
-        }
-    }
+    cudaStream_t qc = (branch && circ_work) ? s->side[0] : st;
+    cudaStream_t qg = (branch && poly_work) ? s->side[1] : st;
 
     // ---- polygon chain: centre (polygon.rs:219) -> own links (polygon.rs:220-222) -> AABB + obstacle bins
     PolyArgs pa{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_static.p, nPoly, s->d_poly_center.p,
@@ -662,13 +670,20 @@ int Ops::launch_substep() {
         if (c0 < s->nP)
             LAUNCH(BENDY_K_GRID_BUILD,
                    k2_count<<<cdiv(s->nP - c0, 256), 256, 0, st>>>(pos, c0, s->nP, prm, s->n_cells, s->d_cell_count.p));
-        LAUNCH(BENDY_K_GRID_BUILD,
-               k2_tile_reduce<<<cdiv(s->n_scan_tiles, 8), 256, 0, st>>>(s->d_cell_count.p, s->n_scan_tiles, s->d_tile_sum.p));
-        LAUNCH(BENDY_K_GRID_BUILD,
-               k2_scan<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p));
+        if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->scan_fused_capacity * 85) {
+            // every scan CTA fits on the device at once (15% spare; side-branch kernels finish on their own)
+            LAUNCH(BENDY_K_GRID_BUILD, k2_scan_fused<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(
+                                           s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
+        } else {
+            LAUNCH(BENDY_K_GRID_BUILD, k2_tile_reduce<<<cdiv(s->n_scan_tiles, 8), 256, 0, st>>>(
+                                           s->d_cell_count.p, s->n_scan_tiles, s->d_tile_sum.p));
+            LAUNCH(BENDY_K_GRID_BUILD, k2_scan<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->d_tile_sum.p,
+                                                                                         s->d_cell_start.p));
+        }
 #define SCATTER(ID, AG)                                                                                              \
     LAUNCH(BENDY_K_GRID_BUILD, k2_scatter<ID, AG><<<cdiv(s->nP, 256), 256, 0, st>>>(                                  \
-                                   pos, s->nP, prm, s->n_cells, s->d_cell_start.p, s->d_sorted_pos.p, s->d_slot_of.p,  \
+                                   pos, s->nP, prm, s->n_cells, s->d_cell_start.p, s->d_scan_barrier.p,            \
+                                   s->d_sorted_pos.p, s->d_slot_of.p,                                                \
                                    s->d_sorted_id.p))
         if (K && s->scatter_agg)
             SCATTER(true, true);
@@ -694,7 +709,7 @@ int Ops::launch_substep() {
     K4Args k4{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_center.p, s->d_poly_box.p, s->d_poly_tiles.p};
     K1Args k1{pos,         s->d_prev.p,    s->accel_pending ? s->d_accel.p : nullptr, dk,
               s->d_crad.p, s->d_gstatic.p, s->nP, s->nC, s->N};
-    uint32_t k1_first = 0;  // first point still to be integrated by K1
+    const bool acc = s->accel_pending;
     if (discs) {
         // narrowphase + polygon contact + bounds + integrate for the free particles, fused
         K2Args a{pos,     s->d_prev.p,   dk,    s->d_slot_of.p, s->d_sorted_id.p, s->d_sorted_pos.p, s->d_cell_start.p, s->n_cells,
@@ -709,39 +724,65 @@ int Ops::launch_substep() {
             LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<false, true><<<blocks, 128, 0, st>>>(a, k4, prm));
         else
             LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<false, false><<<blocks, 128, 0, st>>>(a, k4, prm));
-        if (s->nC)
-            LAUNCH(BENDY_K_CIRCLES, k2_circle_apply<<<cdiv(s->nC, 128), 128, 0, st>>>(pos + s->nP, s->d_circ_acc.p, s->nC,
-                                                                                       s->d_circ_tile_count.p, s->n_circ_tiles));
-        k1_first = s->nP;
-    } else if (contact) {
+        // tails: circles (apply + bounds + integrate) and polygon points (bounds + integrate), each
+        // behind the narrowphase on its own branch
+        if (branch && (qc != st || qg != st)) CK(cudaEventRecord(s->ev_main, st));
+        if (s->nC) {
+            if (qc != st) CK(cudaStreamWaitEvent(qc, s->ev_main, 0));
+            const uint32_t blocks_c = cdiv(s->nC, 128);
+#define CTAIL(A, KK)                                                                                         \
+    LAUNCH(BENDY_K_CIRCLES, k_circle_tail<A, KK, true><<<blocks_c, 128, 0, qc>>>(k1, s->d_circ_acc.p,        \
+                                                                                 s->d_circ_tile_count.p,   \
+                                                                                 s->n_circ_tiles, prm))
+            if (acc && K)
+                CTAIL(true, true);
+            else if (acc)
+                CTAIL(true, false);
+            else if (K)
+                CTAIL(false, true);
+            else
+                CTAIL(false, false);
+#undef CTAIL
+        }
+        if (s->nG) {
+            if (qg != st) CK(cudaStreamWaitEvent(qg, s->ev_main, 0));
+            const uint32_t first = s->nP + s->nC, n = s->nG, blocks_g = cdiv(n, 256);
+            if (acc && K)
+                LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, true><<<blocks_g, 256, 0, qg>>>(k1, first, n, prm));
+            else if (acc)
+                LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, false><<<blocks_g, 256, 0, qg>>>(k1, first, n, prm));
+            else if (K)
+                LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, true><<<blocks_g, 256, 0, qg>>>(k1, first, n, prm));
+            else
+                LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, false><<<blocks_g, 256, 0, qg>>>(k1, first, n, prm));
+        }
+        return BENDY_OK;
+    }
+    if (contact) {
         if (K)
             LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<true><<<cdiv(s->nP, 128), 128, 0, st>>>(pos, dk, s->nP, k4, prm));
         else
             LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<false><<<cdiv(s->nP, 128), 128, 0, st>>>(pos, dk, s->nP, k4, prm));
     }
-    // ---- solve_boundary_collisions + update_positions (solver.rs:113-114), gravity fused
-    if (k1_first == 0) {
+    // ---- solve_boundary_collisions + update_positions (solver.rs:113-114), gravity fused: all points
+    {
         uint32_t blocks = cdiv(s->Npad / 2, 256);
         if (blocks) {
-            if (s->accel_pending && K)
+            if (acc && K)
                 LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, true><<<blocks, 256, 0, st>>>(k1, prm));
-            else if (s->accel_pending)
+            else if (acc)
                 LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, false><<<blocks, 256, 0, st>>>(k1, prm));
             else if (K)
                 LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, true><<<blocks, 256, 0, st>>>(k1, prm));
             else
                 LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, false><<<blocks, 256, 0, st>>>(k1, prm));
         }
-    } else if (s->N > k1_first) {
-        const uint32_t n = s->N - k1_first, blocks = cdiv(n, 256);
-        if (s->accel_pending && K)
-            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, true><<<blocks, 256, 0, st>>>(k1, k1_first, n, prm));
-        else if (s->accel_pending)
-            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, false><<<blocks, 256, 0, st>>>(k1, k1_first, n, prm));
-        else if (K)
-            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, true><<<blocks, 256, 0, st>>>(k1, k1_first, n, prm));
-        else
-            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, false><<<blocks, 256, 0, st>>>(k1, k1_first, n, prm));
+        // the next substep's circle / polygon chains must see the integrated state
+        if (branch) {
+            CK(cudaEventRecord(s->ev_main, st));
+            if (qc != st) CK(cudaStreamWaitEvent(qc, s->ev_main, 0));
+            if (qg != st) CK(cudaStreamWaitEvent(qg, s->ev_main, 0));
+        }
     }
     return BENDY_OK;
 }
@@ -753,9 +794,23 @@ int Ops::build_graph(uint32_t substeps) {
     s->capturing = true;
     s->count_in_capture = 0;
     int rc = BENDY_OK;
-    for (uint32_t k = 0; k < substeps && rc == BENDY_OK; k++) rc = launch_substep();
+    // fork the circle / polygon branches off the main stream once; join them at the end
+    const bool use_c = s->nC > 0, use_g = !s->polys.empty();
+    cudaError_t ce = cudaSuccess;
+    if (use_c || use_g) ce = cudaEventRecord(s->ev_fork, s->stream);
+    if (ce == cudaSuccess && use_c) ce = cudaStreamWaitEvent(s->side[0], s->ev_fork, 0);
+    if (ce == cudaSuccess && use_g) ce = cudaStreamWaitEvent(s->side[1], s->ev_fork, 0);
+    for (uint32_t k = 0; k < substeps && rc == BENDY_OK && ce == cudaSuccess; k++) rc = launch_substep();
+    if (ce == cudaSuccess && use_c) ce = cudaEventRecord(s->ev_join[0], s->side[0]);
+    if (ce == cudaSuccess && use_c) ce = cudaStreamWaitEvent(s->stream, s->ev_join[0], 0);
+    if (ce == cudaSuccess && use_g) ce = cudaEventRecord(s->ev_join[1], s->side[1]);
+    if (ce == cudaSuccess && use_g) ce = cudaStreamWaitEvent(s->stream, s->ev_join[1], 0);
     s->capturing = false;
     cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    if (ce != cudaSuccess && rc == BENDY_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return fail_cuda(ce, "graph branch fork/join", __LINE__);
+    }
     if (rc) {
         if (graph) cudaGraphDestroy(graph);
         return rc;
@@ -817,7 +872,7 @@ bendy_solver::~bendy_solver() {
             if (prm_ring_ev[i]) cudaEventDestroy(prm_ring_ev[i]);
         cudaFreeHost(h_prm_ring);
     }
-    for (cudaEvent_t e : {ev_fork, ev_join[0], ev_join[1]})
+    for (cudaEvent_t e : {ev_fork, ev_join[0], ev_join[1], ev_main})
         if (e) cudaEventDestroy(e);
     for (cudaStream_t q : side)
         if (q) cudaStreamDestroy(q);
@@ -876,6 +931,7 @@ bendy_solver *bendy_create(int device) {
         (e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&s->ev_join[0], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&s->ev_join[1], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&s->t0)) != cudaSuccess || (e = cudaEventCreate(&s->t1)) != cudaSuccess) {
         g_last_error = std::string("CUDA init failed: ") + cudaGetErrorString(e);
         return nullptr;
