@@ -24,7 +24,7 @@ ERR_NAMES = {-1: "BENDY_ERR_ARG", -2: "BENDY_ERR_LINK", -3: "BENDY_ERR_CUDA", -4
              -5: "BENDY_ERR_NO_DEVICE"}
 
 K_CLASSES = ["integrate", "links_local", "links_global", "links_circle", "grid_build", "narrowphase", "circles",
-             "poly_prep", "poly_contact", "fused"]
+             "poly_prep", "poly_contact", "halo"]
 
 
 class ScheduleInfo(C.Structure):
@@ -99,6 +99,12 @@ def signatures():
         "bendy_get_stream": (vp, [vp]),
         "bendy_get_device": (i, [vp]),
         "bendy_get_device_buffers": (i, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]),
+        "bendy_halo_configure": (i, [vp, u32, fl, fl]),
+        "bendy_nccl_unique_id": (i, [vp]),
+        "bendy_halo_comm_nccl": (i, [vp, vp, i, i]),
+        "bendy_halo_connect_local": (i, [vp, vp]),
+        "bendy_update_group": (i, [C.POINTER(vp), i, u32, fl, fl, fl, fl, fl, fl, fl]),
+        "bendy_halo_stats": (i, [vp, u32p, u32p, u32p]),
         "bendy_plan_links": (i, [sz, u32p, sz, u32, u32, u32p, u32p, u32p, u32p, C.POINTER(ScheduleInfo)]),
     }
     return _SIGS

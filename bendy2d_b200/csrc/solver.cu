@@ -5,6 +5,8 @@
 // (solver.rs:109-115): gravity -> links -> dynamic collisions -> bounds -> integrate, with gravity
 // fused into the integrate kernel (acc is zero between substeps: particle.rs:24, solver.rs:110).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -59,6 +61,52 @@ struct PolyHost {
     bool is_static = false;
     float2 center = {0.f, 0.f};
 };
+
+// NCCL is reached through dlopen so that libbendy2d_b200.so has no link-time dependency on it; in
+// a torch process the already-loaded libnccl.so.2 (same SONAME) is reused.
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+    bool load() {
+        if (lib) return true;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) {
+            err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+            return false;
+        }
+#define NCCL_SYM(field, name)                                                    \
+    field = reinterpret_cast<decltype(field)>(dlsym(lib, name));                 \
+    if (!field) {                                                                \
+        err = std::string("libnccl is missing ") + name;                         \
+        lib = nullptr;                                                           \
+        return false;                                                            \
+    }
+        NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+        NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        NCCL_SYM(Send, "ncclSend")
+        NCCL_SYM(Recv, "ncclRecv")
+        NCCL_SYM(GroupStart, "ncclGroupStart")
+        NCCL_SYM(GroupEnd, "ncclGroupEnd")
+        NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+enum Phase { PHASE_ALL = 0, PHASE_A = 1, PHASE_B = 2 };
 
 struct PendingEvent {
     int cls;
@@ -132,6 +180,19 @@ struct bendy_solver {
     uint32_t n_poly_tiles = 0;
     DevBuf<int> d_flags;
 
+    // ---------------- spatial strips (multi-GPU): ghost disc slots + halo exchange
+    uint32_t nOwned = 0;      // free particles owned by this solver (== p_pos.size())
+    uint32_t ghost_cap = 0;   // ghost slots per side; discs [nOwned, nOwned+cap) come from the left neighbour,
+                              // [nOwned+cap, nOwned+2cap) from the right one
+    bool halo_on = false;
+    float halo_xl = -INFINITY, halo_xr = INFINITY;
+    DevBuf<float2> d_send[2];
+    DevBuf<uint32_t> d_send_cnt;
+    ncclComm_t nccl_comm = nullptr;
+    int comm_rank = -1, comm_world = 0;
+    bendy_solver *peer[2] = {nullptr, nullptr};  // same-process transport (1-GPU emulation of strips)
+    cudaEvent_t ev_phase_a = nullptr, ev_xchg = nullptr;
+
     // ---------------- per-update params
     DevBuf<StepParams> d_prm;
     StepParams prm{};
@@ -195,7 +256,8 @@ struct Ops {  // helper with access to the solver; keeps bendy_solver a plain st
     int configure(float dt, float gx, float gy, float bx, float by, float bw, float bh);
     int grid_for(float bx, float by, float bw, float bh, StepParams *p, uint32_t *ncells);
     int enqueue_substeps(uint32_t count);
-    int launch_substep();
+    int launch_substep(int phase = PHASE_ALL);
+    int halo_exchange_nccl();
     int build_graph(uint32_t substeps);
     void drop_graph();
     int flush_events();
@@ -289,7 +351,7 @@ int Ops::pull() {
         std::vector<float2> &P = which == 0 ? s->p_pos : s->p_prev;
         std::vector<float2> &Cc = which == 0 ? s->c_pos : s->c_prev;
         std::vector<float2> &G = which == 0 ? s->g_pos : s->g_prev;
-        for (uint32_t i = 0; i < s->nP; i++) P[i] = tmp[s->plan_p.rank[i]];
+        for (uint32_t i = 0; i < s->nOwned; i++) P[i] = tmp[s->plan_p.rank[i]];
         for (uint32_t i = 0; i < s->nC; i++) Cc[i] = tmp[s->nP + i];
         for (uint32_t i = 0; i < s->nG; i++) G[i] = tmp[s->nP + s->nC + i];
     }
@@ -344,13 +406,18 @@ int Ops::rebuild() {
     if (int rc = bind()) return rc;
     if (int rc = pull()) return rc;
     drop_graph();
-    s->nP = (uint32_t)s->p_pos.size();
+    s->nOwned = (uint32_t)s->p_pos.size();
+    s->nP = s->nOwned + (s->halo_on ? 2 * s->ghost_cap : 0);  // disc slots = owned + ghosts
     s->nC = (uint32_t)s->c_pos.size();
+    if (s->halo_on && (s->nC || !s->polys.empty() || !s->p_k.empty()))
+        return fail(BENDY_ERR_UNSUPPORTED,
+                    "strips (halo exchange) support free particles and particle links only: no circles, polygons "
+                    "or inverse masses in a sharded solver yet");
     s->nG = (uint32_t)s->g_pos.size();
     s->N = s->nP + s->nC + s->nG;
     s->Npad = (s->N + 1u) & ~1u;
     std::string perr;
-    if (!plan_links(s->nP, s->pl_ab.data(), s->pl_len.data(), s->pl_len.size(), s->plan_params, false, &s->plan_p,
+    if (!plan_links(s->nOwned, s->pl_ab.data(), s->pl_len.data(), s->pl_len.size(), s->plan_params, false, &s->plan_p,
                     &perr))
         return fail(BENDY_ERR_UNSUPPORTED, perr);
     // polygon-internal links (polygon.rs:218-223) use polygon-local indices: rebase to the polygon
@@ -368,10 +435,11 @@ int Ops::rebuild() {
     }
     // ---- state upload (internal order)
     std::vector<float2> pos(s->Npad), prev(s->Npad);
-    for (uint32_t i = 0; i < s->nP; i++) {
+    for (uint32_t i = 0; i < s->nOwned; i++) {
         pos[s->plan_p.rank[i]] = s->p_pos[i];
         prev[s->plan_p.rank[i]] = s->p_prev[i];
     }
+    for (uint32_t i = s->nOwned; i < s->nP; i++) pos[i] = prev[i] = make_float2(NAN, NAN);  // empty ghost slots
     std::copy(s->c_pos.begin(), s->c_pos.end(), pos.begin() + s->nP);
     std::copy(s->c_prev.begin(), s->c_prev.end(), prev.begin() + s->nP);
     std::copy(s->g_pos.begin(), s->g_pos.end(), pos.begin() + s->nP + s->nC);
@@ -392,7 +460,7 @@ int Ops::rebuild() {
     if (s->has_k) {
         std::vector<float> k(s->Npad, 1.0f);
         if (!s->p_k.empty())
-            for (uint32_t i = 0; i < s->nP; i++) k[s->plan_p.rank[i]] = s->p_k[i];
+            for (uint32_t i = 0; i < s->nOwned; i++) k[s->plan_p.rank[i]] = s->p_k[i];
         if (!s->c_k.empty()) std::copy(s->c_k.begin(), s->c_k.end(), k.begin() + s->nP);
         CK(upload(s->d_k, k, s->stream));
     }
@@ -452,6 +520,14 @@ int Ops::rebuild() {
         CK(s->d_slot_of.ensure(s->nP));
         CK(s->d_sorted_pos.ensure(s->nP));
     }
+    if (s->halo_on && s->ghost_cap) {
+        for (int side = 0; side < 2; side++) CK(s->d_send[side].ensure(s->ghost_cap));
+        CK(s->d_send_cnt.ensure(4));
+        CK(cudaMemsetAsync(s->d_send_cnt.p, 0, 4 * sizeof(uint32_t), s->stream));
+        k_halo_clear<<<cdiv(s->ghost_cap, 256), 256, 0, s->stream>>>(s->d_send[0].p, s->d_send[1].p, s->d_send_cnt.p,
+                                                                     s->ghost_cap);
+        CK(cudaGetLastError());
+    }
     if (s->nC) {
         CK(s->d_circ_acc.ensure(2 * (size_t)s->nC));
         CK(cudaMemsetAsync(s->d_circ_acc.p, 0, 2 * (size_t)s->nC * sizeof(unsigned long long), s->stream));
@@ -505,6 +581,8 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
     p.hi_x = bx + bw;  // particle.rs:32
     p.hi_y = by + bh;  // particle.rs:41
     p.rp = s->particle_radius;
+    p.halo_xl = s->halo_on ? s->halo_xl : -INFINITY;
+    p.halo_xr = s->halo_on ? s->halo_xr : INFINITY;
     uint32_t ncells = 0;
     const bool discs = s->particle_radius > 0.f && s->nP > 0;
     if (discs) {
@@ -585,7 +663,37 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
 // Free particles, circles and polygon points are disjoint worlds until the collision phase
 // (solver.rs:143-153), so while capturing a graph the circle and polygon chains run as parallel
 // branches beside the particle chain; eager (profiling) launches are simply serial.
-int Ops::launch_substep() {
+int Ops::halo_exchange_nccl() {
+    if (!s->nccl_comm) return BENDY_OK;  // a single strip: nothing to exchange
+    const size_t nflt = 2 * (size_t)s->ghost_cap;
+    float2 *ghost = s->d_pos.p + s->nOwned;
+    const int left = s->comm_rank - 1, right = s->comm_rank + 1;
+    auto ck = [&](ncclResult_t r, const char *what) -> int {
+        if (r == ncclSuccess) return BENDY_OK;
+        s->sticky = BENDY_ERR_CUDA;
+        return fail(BENDY_ERR_CUDA, std::string("NCCL error in ") + what + ": " + g_nccl.GetErrorString(r));
+    };
+    if (int rc = ck(g_nccl.GroupStart(), "ncclGroupStart")) return rc;
+    if (left >= 0) {
+        if (int rc = ck(g_nccl.Send(s->d_send[0].p, nflt, ncclFloat, left, s->nccl_comm, s->stream), "ncclSend")) return rc;
+        if (int rc = ck(g_nccl.Recv(ghost, nflt, ncclFloat, left, s->nccl_comm, s->stream), "ncclRecv")) return rc;
+    }
+    if (right < s->comm_world) {
+        if (int rc = ck(g_nccl.Send(s->d_send[1].p, nflt, ncclFloat, right, s->nccl_comm, s->stream), "ncclSend")) return rc;
+        if (int rc = ck(g_nccl.Recv(ghost + s->ghost_cap, nflt, ncclFloat, right, s->nccl_comm, s->stream), "ncclRecv"))
+            return rc;
+    }
+    if (int rc = ck(g_nccl.GroupEnd(), "ncclGroupEnd")) return rc;
+    if (s->capturing)
+        s->count_in_capture++;
+    else
+        s->launches++, s->k_launches[BENDY_K_HALO]++;
+    return BENDY_OK;
+}
+
+// phase: PHASE_ALL = the whole substep (NCCL exchange in-stream); PHASE_A = up to the halo packing;
+// PHASE_B = from the ghost histogram on (bendy_update_group moves the halo between A and B).
+int Ops::launch_substep(int phase) {
     cudaStream_t st = s->stream;
     const StepParams *prm = s->d_prm.p;
     const bool K = s->has_k;
@@ -595,6 +703,14 @@ int Ops::launch_substep() {
     const bool discs = s->particle_radius > 0.f && s->nP;
     const bool branch = s->capturing;
     const float *dk = K ? s->d_k.p : nullptr;
+    const bool halo = s->halo_on && discs && s->ghost_cap > 0;
+    const K3CountArgs ca{prm,
+                         s->n_cells,
+                         s->d_cell_count.p,
+                         halo ? s->d_send[0].p : nullptr,
+                         halo ? s->d_send[1].p : nullptr,
+                         halo ? s->d_send_cnt.p : nullptr,
+                         halo ? s->ghost_cap : 0u};
 
     auto run_plan = [&](const LinkPlan &P, uint32_t base, const uint32_t *d_ps, const uint32_t *d_cs,
                         const LocalLink *d_l, const GlobalLink *d_g, cudaStream_t q, bool fuse_count) -> int {
@@ -602,17 +718,18 @@ int Ops::launch_substep() {
             uint32_t maxp = 0;
             for (uint32_t p = 0; p < P.n_parts(); p++) maxp = std::max(maxp, P.part_start[p + 1] - P.part_start[p]);
             size_t smem = (size_t)maxp * (K ? 12 : 8);
-            K3CountArgs ca{prm, s->n_cells, s->d_cell_count.p};
             const uint32_t T = s->k3_threads;
             const uint32_t np = P.n_parts(), C = P.n_local_colours;
-            if (K && fuse_count)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, true><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+            if (fuse_count && halo)  // strips: no inverse masses (checked in rebuild)
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, true><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+            else if (K && fuse_count)
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, true, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
             else if (K)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, false, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
             else if (fuse_count)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
             else
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, false, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
         }
         for (uint32_t c = 0; c < P.n_global_colours(); c++) {
             uint32_t l0 = P.gcolour_start[c], l1 = P.gcolour_start[c + 1];
@@ -629,12 +746,13 @@ int Ops::launch_substep() {
     // circle chain runs on side[0], the polygon chain on side[1].  Their tails (integrate) of
     // substep k are queued behind the narrowphase of substep k and overlap the particle chain
     // of substep k+1, which never touches circle or polygon state before ITS join.
-    const bool circ_work = s->nC > 0;
     const bool poly_work = nPoly > 0;
-    cudaStream_t qc = (branch && circ_work) ? s->side[0] : st;
-    cudaStream_t qg = (branch && poly_work) ? s->side[1] : st;
 
+    if (phase == PHASE_B) goto phase_b;
+    {
     // ---- polygon chain: centre (polygon.rs:219) -> own links (polygon.rs:220-222) -> AABB + obstacle bins
+    cudaStream_t qc = (branch && s->nC > 0) ? s->side[0] : st;
+    cudaStream_t qg = (branch && nPoly > 0) ? s->side[1] : st;
     PolyArgs pa{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_static.p, nPoly, s->d_poly_center.p,
                 s->d_poly_box.p,     s->d_poly_tiles.p, s->d_flags.p};
     if (poly_work) {
@@ -665,11 +783,31 @@ int Ops::launch_substep() {
     const bool fuse_count = discs && s->plan_p.n_global_colours() == 0 && n_in_parts > 0;
     if (int rc = run_plan(s->plan_p, 0, s->d_part_start.p, s->d_part_cs.p, s->d_local.p, s->d_global.p, st, fuse_count))
         return rc;
-    if (discs) {
+    if (discs) {  // histogram (+ halo packing) of the owned discs the link kernel did not cover
         const uint32_t c0 = fuse_count ? n_in_parts : 0u;
-        if (c0 < s->nP)
-            LAUNCH(BENDY_K_GRID_BUILD,
-                   k2_count<<<cdiv(s->nP - c0, 256), 256, 0, st>>>(pos, c0, s->nP, prm, s->n_cells, s->d_cell_count.p));
+        if (c0 < s->nOwned) {
+            if (halo)
+                LAUNCH(BENDY_K_GRID_BUILD, k2_count<true><<<cdiv(s->nOwned - c0, 256), 256, 0, st>>>(pos, c0, s->nOwned, ca));
+            else
+                LAUNCH(BENDY_K_GRID_BUILD, k2_count<false><<<cdiv(s->nOwned - c0, 256), 256, 0, st>>>(pos, c0, s->nOwned, ca));
+        }
+    }
+    }
+    if (phase == PHASE_A) {
+        CK(cudaEventRecord(s->ev_phase_a, st));
+        return BENDY_OK;
+    }
+    if (halo && phase == PHASE_ALL)
+        if (int rc = halo_exchange_nccl()) return rc;
+phase_b:
+    if (halo) {  // my send buffers were consumed: reset them; then the received ghosts join the histogram
+        LAUNCH(BENDY_K_HALO, k_halo_clear<<<cdiv(s->ghost_cap, 256), 256, 0, st>>>(s->d_send[0].p, s->d_send[1].p,
+                                                                                   s->d_send_cnt.p, s->ghost_cap));
+        LAUNCH(BENDY_K_GRID_BUILD, k2_count<false><<<cdiv(s->nP - s->nOwned, 256), 256, 0, st>>>(pos, s->nOwned, s->nP, ca));
+    }
+    cudaStream_t qc = (branch && s->nC > 0) ? s->side[0] : st;
+    cudaStream_t qg = (branch && nPoly > 0) ? s->side[1] : st;
+    if (discs) {
         if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->scan_fused_capacity * 85) {
             // every scan CTA fits on the device at once (15% spare; side-branch kernels finish on their own)
             LAUNCH(BENDY_K_GRID_BUILD, k2_scan_fused<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(
@@ -713,9 +851,9 @@ int Ops::launch_substep() {
     if (discs) {
         // narrowphase + polygon contact + bounds + integrate for the free particles, fused
         K2Args a{pos,     s->d_prev.p,   dk,    s->d_slot_of.p, s->d_sorted_id.p, s->d_sorted_pos.p, s->d_cell_start.p, s->n_cells,
-                 s->nP,   s->nP,         s->nC, s->d_crad.p,             s->d_circ_tile_count.p,  s->d_circ_tile_ids.p,
+                 s->nP,   s->nOwned,     s->nC, s->d_crad.p,             s->d_circ_tile_count.p,  s->d_circ_tile_ids.p,
                  s->d_circ_acc.p};
-        const uint32_t blocks = cdiv(s->nP, 128);
+        const uint32_t blocks = cdiv(s->nOwned, 128);
         if (K && contact)
             LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<true, true><<<blocks, 128, 0, st>>>(a, k4, prm));
         else if (K)
@@ -872,7 +1010,10 @@ bendy_solver::~bendy_solver() {
             if (prm_ring_ev[i]) cudaEventDestroy(prm_ring_ev[i]);
         cudaFreeHost(h_prm_ring);
     }
-    for (cudaEvent_t e : {ev_fork, ev_join[0], ev_join[1], ev_main})
+    if (nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(nccl_comm);
+    for (int sd = 0; sd < 2; sd++)
+        if (peer[sd]) peer[sd]->peer[1 - sd] = nullptr;
+    for (cudaEvent_t e : {ev_fork, ev_join[0], ev_join[1], ev_main, ev_phase_a, ev_xchg})
         if (e) cudaEventDestroy(e);
     for (cudaStream_t q : side)
         if (q) cudaStreamDestroy(q);
@@ -932,6 +1073,8 @@ bendy_solver *bendy_create(int device) {
         (e = cudaEventCreateWithFlags(&s->ev_join[0], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&s->ev_join[1], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&s->ev_phase_a, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&s->ev_xchg, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&s->t0)) != cudaSuccess || (e = cudaEventCreate(&s->t1)) != cudaSuccess) {
         g_last_error = std::string("CUDA init failed: ") + cudaGetErrorString(e);
         return nullptr;
@@ -1408,6 +1551,135 @@ int bendy_get_device_buffers(bendy_solver *s, void **pos, void **prev, size_t *n
     if (pos) *pos = s->d_pos.p;
     if (prev) *prev = s->d_prev.p;
     if (n_points) *n_points = s->N;
+    return BENDY_OK;
+}
+
+// ---- spatial strips: halo exchange ----------------------------------------------------------------
+int bendy_halo_configure(bendy_solver *s, uint32_t ghost_cap, float x_left, float x_right) {
+    NEED(s);
+    OPS;
+    if (ghost_cap > 0x3FFFFFFFu) return ops.fail(BENDY_ERR_ARG, "ghost capacity too large");
+    if (int rc = edit_begin(s)) return rc;
+    s->halo_on = ghost_cap > 0;
+    s->ghost_cap = ghost_cap;
+    s->halo_xl = x_left, s->halo_xr = x_right;
+    s->prm_valid = false;
+    edit_end(s);
+    return BENDY_OK;
+}
+
+int bendy_nccl_unique_id(void *out128) {
+    if (!out128) return BENDY_ERR_ARG;
+    if (!g_nccl.load()) {
+        g_last_error = g_nccl.err;
+        return BENDY_ERR_UNSUPPORTED;
+    }
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) {
+        g_last_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r);
+        return BENDY_ERR_CUDA;
+    }
+    std::memcpy(out128, &id, sizeof id);
+    return BENDY_OK;
+}
+
+int bendy_halo_comm_nccl(bendy_solver *s, const void *unique_id128, int rank, int world) {
+    NEED(s);
+    OPS;
+    if (!unique_id128 || rank < 0 || rank >= world) return ops.fail(BENDY_ERR_ARG, "bendy_halo_comm_nccl: bad arguments");
+    if (!g_nccl.load()) return ops.fail(BENDY_ERR_UNSUPPORTED, g_nccl.err);
+    if (int rc = ops.bind()) return rc;
+    if (s->nccl_comm) {
+        g_nccl.CommDestroy(s->nccl_comm);
+        s->nccl_comm = nullptr;
+    }
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id128, sizeof id);
+    ncclResult_t r = g_nccl.CommInitRank(&s->nccl_comm, world, id, rank);
+    if (r != ncclSuccess) return ops.fail(BENDY_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+    s->comm_rank = rank, s->comm_world = world;
+    ops.drop_graph();
+    return BENDY_OK;
+}
+
+int bendy_halo_connect_local(bendy_solver *left, bendy_solver *right) {
+    if (!left || !right || left == right) return BENDY_ERR_ARG;
+    if (left->ghost_cap != right->ghost_cap || !left->halo_on || !right->halo_on) {
+        g_last_error = left->err = "bendy_halo_connect_local: both strips need the same ghost capacity";
+        return BENDY_ERR_ARG;
+    }
+    left->peer[1] = right;
+    right->peer[0] = left;
+    return BENDY_OK;
+}
+
+int bendy_halo_stats(bendy_solver *s, uint32_t *sent_left, uint32_t *sent_right, uint32_t *overflow) {
+    NEED(s);
+    OPS;
+    uint32_t h[4] = {0, 0, 0, 0};
+    if (s->d_send_cnt.p) {
+        if (int rc = ops.bind()) return rc;
+        CK(cudaStreamSynchronize(s->stream));
+        CK(cudaMemcpy(h, s->d_send_cnt.p, sizeof h, cudaMemcpyDeviceToHost));
+    }
+    if (sent_left) *sent_left = h[0];
+    if (sent_right) *sent_right = h[1];
+    if (overflow) *overflow = h[2];
+    return BENDY_OK;
+}
+
+// Lock-step stepping of several strips that live in ONE process (same-process transport): for every
+// substep all strips run phase A, the halos are copied device-to-device, all strips run phase B.
+// This is the 1-GPU emulation of the multi-GPU path; the arithmetic is that of bendy_update.
+int bendy_update_group(bendy_solver **group, int n, uint32_t n_updates, float dt, float gx, float gy, float bx,
+                       float by, float bw, float bh) {
+    if (!group || n <= 0) return BENDY_ERR_ARG;
+    for (int k = 0; k < n; k++) {
+        bendy_solver *s = group[k];
+        NEED(s);
+        OPS;
+        if (int rc = ops.ensure_ready()) return rc;
+        if (int rc = ops.flush_events()) return rc;
+        float delta = dt * (1.0f / (float)s->sub_steps);
+        if (int rc = ops.configure(delta, gx, gy, bx, by, bw, bh)) return rc;
+        if (s->sub_steps != group[0]->sub_steps) return ops.fail(BENDY_ERR_ARG, "group members need equal sub_steps");
+    }
+    const uint32_t total = n_updates * group[0]->sub_steps;
+    for (uint32_t step = 0; step < total; step++) {
+        for (int k = 0; k < n; k++) {
+            bendy_solver *s = group[k];
+            OPS;
+            if (int rc = ops.bind()) return rc;
+            if (int rc = ops.launch_substep(PHASE_A)) return rc;
+            if (!(s->halo_on && s->particle_radius > 0.f && s->nP)) CK(cudaEventRecord(s->ev_phase_a, s->stream));
+        }
+        for (int k = 0; k < n; k++) {
+            bendy_solver *s = group[k];
+            OPS;
+            if (int rc = ops.bind()) return rc;
+            const size_t bytes = (size_t)s->ghost_cap * sizeof(float2);
+            for (int side = 0; side < 2; side++) {
+                bendy_solver *p = s->peer[side];
+                if (!p || !bytes) continue;
+                CK(cudaStreamWaitEvent(s->stream, p->ev_phase_a, 0));
+                // my left ghosts = the left peer's right-going send buffer, and vice versa
+                CK(cudaMemcpyAsync(s->d_pos.p + s->nOwned + (size_t)side * s->ghost_cap, p->d_send[1 - side].p, bytes,
+                                   cudaMemcpyDeviceToDevice, s->stream));
+            }
+            CK(cudaEventRecord(s->ev_xchg, s->stream));
+        }
+        for (int k = 0; k < n; k++) {
+            bendy_solver *s = group[k];
+            OPS;
+            if (int rc = ops.bind()) return rc;
+            for (int side = 0; side < 2; side++)
+                if (s->peer[side]) CK(cudaStreamWaitEvent(s->stream, s->peer[side]->ev_xchg, 0));
+            if (int rc = ops.launch_substep(PHASE_B)) return rc;
+            s->accel_pending = false;
+            s->host_valid = false;
+        }
+    }
     return BENDY_OK;
 }
 

@@ -55,6 +55,7 @@ class Scene:
     polygons: List[np.ndarray] = field(default_factory=list)  # explicit vertex lists (Polygon::new)
     polygons_static: List[bool] = field(default_factory=list)
     timed_substeps: int = 200
+    body_of: Optional[np.ndarray] = None  # body (connected component) id per particle, if the generator knows it
 
     # -- sizes
     @property
@@ -230,7 +231,7 @@ def softbody_field(bodies_x: int, bodies_y: int, bounds, origin, n_circles: int,
             statics.append(True)
     return Scene(name, bounds, particle_radius=0.1, polygon_contact=n_polygons > 0, particles=pos, links_ab=ab,
                  links_len=ln, circles_pos=circles_pos, circles_r=circles_r, polygons=polys, polygons_static=statics,
-                 timed_substeps=timed)
+                 timed_substeps=timed, body_of=np.repeat(np.arange(len(offs), dtype=np.int64), len(pos0)))
 
 
 def c3_softbody_field(bodies_x: int = 50, bodies_y: int = 40, n_circles: int = 200, n_polygons: int = 500) -> Scene:
@@ -269,8 +270,3 @@ def c5_softbody_field_16m(bodies_x: int = 200, bodies_y: int = 160) -> Scene:
                           f"C5 softbody field {bodies_x * bodies_y} bodies", 100)
 
 
-def strip_of(scene: Scene, rank: int, world: int) -> Scene:
-    """Spatial-strip shard of a softbody-field scene: whole bodies by centroid x, equal body counts."""
-    if world == 1:
-        return scene
-    raise NotImplementedError("strip sharding is built by bendy2d_b200.strips")

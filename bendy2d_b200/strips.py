@@ -1,0 +1,224 @@
+"""Spatial-strip sharding of a scene across the GPUs of one box.
+
+Whole bodies (connected components of the link graph) are assigned to vertical strips of equal
+body count by centroid x.  Every substep each strip sends the owned discs that lie inside its
+neighbours' halo bands; they become read-only ghost discs of the neighbour's broadphase grid.
+The Jacobi contact rule only ever moves a disc on the rank that owns it, so no corrections travel
+back, and because all sums are order-free the sharded run is bit-identical to the 1-GPU run.
+
+  StripSolver      one process per GPU, halo over NCCL (send/recv on the solver's stream, issued by
+                   libbendy2d_b200.so inside the captured substep graph); torch.distributed only
+                   carries the NCCL unique id and the timing reductions.
+  LocalStripGroup  all strips in one process on one GPU (device-to-device halo copies): the
+                   no-cluster stand-in used by the 1-GPU tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, replace
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from .scenes import Scene
+from .solver import Solver
+
+f32 = np.float32
+
+
+def body_ids(scene: Scene) -> np.ndarray:
+    """Connected components of the particle-link graph (unlinked particles are their own body)."""
+    n = scene.n_particles
+    if scene.n_links == 0:
+        return np.arange(n, dtype=np.int64)
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+
+    ab = scene.links_ab.astype(np.int64)
+    g = coo_matrix((np.ones(len(ab), np.int8), (ab[:, 0], ab[:, 1])), shape=(n, n))
+    _, labels = connected_components(g, directed=False)
+    return labels.astype(np.int64)
+
+
+@dataclass
+class StripPart:
+    rank: int
+    world: int
+    scene: Scene              # the local scene (owned bodies only)
+    global_index: np.ndarray  # local particle -> index in the full scene
+    x_left: float             # strip edges (-inf / +inf at the ends of the chain)
+    x_right: float
+    band: float
+    ghost_cap: int
+
+    @property
+    def send_left_below(self) -> float:   # owned discs with x below this go to the left neighbour
+        return float(self.x_left + self.band) if np.isfinite(self.x_left) else float("-inf")
+
+    @property
+    def send_right_above(self) -> float:
+        return float(self.x_right - self.band) if np.isfinite(self.x_right) else float("inf")
+
+
+def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodies: Optional[np.ndarray] = None,
+                    cap_factor: float = 2.0) -> List[StripPart]:
+    """Split `scene` into `world` strips.  Circles / polygons are not sharded yet (SURVEY §8.5
+    scopes strips to the softbody field): they must be absent."""
+    if len(scene.circles_r) or len(scene.polygons):
+        raise ValueError("strip sharding supports free particles and links only")
+    n = scene.n_particles
+    if bodies is None:
+        bodies = scene.body_of if scene.body_of is not None else body_ids(scene)
+    bodies = np.asarray(bodies, np.int64)
+    nb = int(bodies.max()) + 1 if n else 0
+    cnt = np.bincount(bodies, minlength=nb).astype(np.float64)
+    cx = np.bincount(bodies, weights=scene.particles[:, 0].astype(np.float64), minlength=nb) / np.maximum(cnt, 1)
+    xmin = np.full(nb, np.inf)
+    xmax = np.full(nb, -np.inf)
+    np.minimum.at(xmin, bodies, scene.particles[:, 0])
+    np.maximum.at(xmax, bodies, scene.particles[:, 0])
+    order = np.argsort(cx, kind="stable")
+    # equal body counts per strip; edge = midway between the neighbouring groups' centroids
+    cuts = [int(round(k * nb / world)) for k in range(world + 1)]
+    strip_of_body = np.empty(nb, np.int64)
+    edges = [-np.inf]
+    for k in range(world):
+        strip_of_body[order[cuts[k]:cuts[k + 1]]] = k
+        if k + 1 < world:
+            a = cx[order[cuts[k + 1] - 1]] if cuts[k + 1] > cuts[k] else cx[order[max(cuts[k + 1] - 1, 0)]]
+            b = cx[order[min(cuts[k + 1], nb - 1)]]
+            edges.append(0.5 * (a + b))
+    edges.append(np.inf)
+    if band is None:
+        # a body reaches half its width past the edge it was assigned by; + drift allowance + contact range
+        half = 0.5 * float(np.max(xmax - xmin)) if nb else 0.0
+        band = half + 1.0 + 2.0 * scene.particle_radius
+    strip_of_particle = strip_of_body[bodies]
+    parts = []
+    link_strip = strip_of_particle[scene.links_ab[:, 0].astype(np.int64)] if scene.n_links else np.zeros(0, np.int64)
+    for k in range(world):
+        sel = np.nonzero(strip_of_particle == k)[0]
+        remap = np.full(n, -1, np.int64)
+        remap[sel] = np.arange(len(sel))
+        lsel = np.nonzero(link_strip == k)[0]
+        ab = remap[scene.links_ab[lsel].astype(np.int64)]
+        if (ab < 0).any():
+            raise ValueError("a link crosses strips: bodies must be whole")
+        local = replace(scene, name=f"{scene.name} [strip {k}/{world}]", particles=scene.particles[sel].copy(),
+                        links_ab=ab.astype(np.uint32), links_len=scene.links_len[lsel].copy(), body_of=None)
+        xl, xr = edges[k], edges[k + 1]
+        px = local.particles[:, 0]
+        in_band = 0
+        if np.isfinite(xl):
+            in_band = max(in_band, int((px < xl + band).sum()))
+        if np.isfinite(xr):
+            in_band = max(in_band, int((px > xr - band).sum()))
+        parts.append(StripPart(k, world, local, sel, float(xl), float(xr), float(band), 0 if world == 1 else in_band))
+    # both ends of an exchange use the same message size: one capacity for the whole chain
+    cap = int(max(p.ghost_cap for p in parts) * cap_factor) + 1024 if world > 1 else 0
+    for p in parts:
+        p.ghost_cap = cap
+    return parts
+
+
+def _load_part(part: StripPart, device: int) -> Solver:
+    sv = Solver(device)
+    part.scene.load_into(sv)
+    if part.world > 1:
+        sv._ck(sv._L.bendy_halo_configure(sv._h, part.ghost_cap, part.send_left_below, part.send_right_above))
+    return sv
+
+
+class _StripBase:
+    """Solver-like surface shared by both transports (what bench.py and the tests call)."""
+
+    solver: Solver
+    part: StripPart
+
+    def local_scene(self) -> Scene:
+        return self.part.scene
+
+    def halo_stats(self, sv: Optional[Solver] = None):
+        sv = sv or self.solver
+        a, b, o = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        sv._ck(sv._L.bendy_halo_stats(sv._h, C.byref(a), C.byref(b), C.byref(o)))
+        return a.value, b.value, o.value
+
+
+class StripSolver(_StripBase):
+    """One strip per process / GPU; halo over NCCL issued by the C library on its own stream."""
+
+    def __init__(self, scene: Scene, rank: int, world: int, device: int, dist=None, band: Optional[float] = None,
+                 bodies: Optional[np.ndarray] = None):
+        import torch
+
+        self.rank, self.world, self.dist = rank, world, dist
+        self.part = partition_scene(scene, world, band, bodies)[rank]
+        self.solver = _load_part(self.part, device)
+        if world > 1:
+            L = self.solver._L
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = (C.c_ubyte * 128)()
+                if L.bendy_nccl_unique_id(buf) != 0:
+                    raise RuntimeError((L.bendy_last_error(None) or b"").decode())
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            uid = uid.cuda(device) if dist.get_backend() == "nccl" else uid
+            dist.broadcast(uid, src=0)
+            raw = bytes(uid.cpu().tolist())
+            self.solver._ck(L.bendy_halo_comm_nccl(self.solver._h, raw, rank, world))
+
+    # ---- Solver surface
+    def update(self, dt: float, n: int = 1):
+        self.solver.update(dt, n)
+
+    def __getattr__(self, name):  # everything else is the local solver's
+        return getattr(self.solver, name)
+
+    def check_halo(self):
+        l, r, o = self.halo_stats()
+        if o:
+            raise RuntimeError(f"halo overflow on rank {self.rank}: ghost_cap {self.part.ghost_cap}, sent {l}/{r}")
+        return l, r
+
+
+class LocalStripGroup:
+    """All strips of a scene in ONE process on ONE GPU, stepped in lock-step with device-to-device
+    halo copies (bendy_update_group).  Arithmetic and kernels are those of the multi-GPU path."""
+
+    def __init__(self, scene: Scene, n_strips: int, device: int = -1, band: Optional[float] = None,
+                 bodies: Optional[np.ndarray] = None):
+        self.scene = scene
+        self.parts = partition_scene(scene, n_strips, band, bodies)
+        self.solvers = [_load_part(p, device) for p in self.parts]
+        L = self.solvers[0]._L
+        for a, b in zip(self.solvers[:-1], self.solvers[1:]):
+            if L.bendy_halo_connect_local(a._h, b._h) != 0:
+                raise RuntimeError((L.bendy_last_error(None) or b"").decode())
+        self._handles = (C.c_void_p * len(self.solvers))(*[s._h for s in self.solvers])
+
+    def update(self, dt: float, n: int = 1):
+        s0 = self.solvers[0]
+        g, b = s0.gravity, s0.bounds
+        rc = s0._L.bendy_update_group(self._handles, len(self.solvers), n, dt, float(g[0]), float(g[1]),
+                                      float(b.pos[0]), float(b.pos[1]), float(b.size[0]), float(b.size[1]))
+        if rc != 0:
+            for s in self.solvers:
+                s._ck(rc)
+
+    def read_particles(self):
+        pos = np.empty((self.scene.n_particles, 2), f32)
+        prev = np.empty_like(pos)
+        for p, s in zip(self.parts, self.solvers):
+            lp, lq = s.read_particles()
+            pos[p.global_index], prev[p.global_index] = lp, lq
+        return pos, prev
+
+    def halo_stats(self):
+        out = []
+        for s in self.solvers:
+            a, b, o = C.c_uint32(), C.c_uint32(), C.c_uint32()
+            s._ck(s._L.bendy_halo_stats(s._h, C.byref(a), C.byref(b), C.byref(o)))
+            out.append((a.value, b.value, o.value))
+        return out

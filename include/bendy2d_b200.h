@@ -145,7 +145,7 @@ enum {
     BENDY_K_CIRCLES,       /* circle-circle lexicographic pass + circle binning/apply */
     BENDY_K_POLY_PREP,     /* polygon centre / AABB / binning */
     BENDY_K_POLY_CONTACT,  /* K4 particle-polygon closest edge (+ polygon-polygon) */
-    BENDY_K_FUSED,         /* fused integrate+links(+hash) kernel when the schedule allows it */
+    BENDY_K_HALO,          /* strips: halo exchange (NCCL send/recv or peer copy) + send-buffer reset */
     BENDY_K_CLASSES
 };
 /* profile != 0: launch kernels one by one with cudaEvent pairs (slower; for per-kernel timing).
@@ -162,7 +162,28 @@ int bendy_timer_stop(bendy_solver *s, float *ms); /* synchronises */
 void *bendy_get_stream(const bendy_solver *s);
 int bendy_get_device(const bendy_solver *s);
 
-/* ---------------------------------------------------------------- multi-GPU strips (halo exchange) */
+/* ---------------------------------------------------------------- multi-GPU strips (halo exchange)
+ * One process per GPU; each solver owns the bodies of one vertical strip of the world.  Every
+ * substep, after the link pass, owned discs lying left of x_left / right of x_right (the strip
+ * edges moved inwards by the halo band) are packed on the device and sent to the left / right
+ * neighbour, where they occupy read-only ghost slots of the broadphase grid.  No reference
+ * counterpart: the reference is single-threaded (solver.rs:109-188). */
+/* ghost_cap = ghost disc slots per side (0 turns strips off); x_left/x_right = -inf/+inf when there is
+ * no neighbour on that side */
+int bendy_halo_configure(bendy_solver *s, uint32_t ghost_cap, float x_left, float x_right);
+/* rank 0 creates the NCCL id (128 bytes); the host layer (torch.distributed) broadcasts it */
+int bendy_nccl_unique_id(void *out128);
+/* joins the strip communicator: neighbours are rank-1 and rank+1; send/recv run on the solver's stream
+ * inside the captured substep graph */
+int bendy_halo_comm_nccl(bendy_solver *s, const void *unique_id128, int rank, int world);
+/* same-process transport between two neighbouring strips (1-GPU emulation, tests) */
+int bendy_halo_connect_local(bendy_solver *left, bendy_solver *right);
+/* lock-step update of several same-process strips (phase A | halo copy | phase B per substep) */
+int bendy_update_group(bendy_solver **group, int n, uint32_t n_updates, float dt, float gx, float gy, float bx,
+                       float by, float bw, float bh);
+/* discs packed for each neighbour in the last substep; overflow != 0 means ghost_cap was too small */
+int bendy_halo_stats(bendy_solver *s, uint32_t *sent_left, uint32_t *sent_right, uint32_t *overflow);
+
 /* Device pointers of the internal SoA (pos, prev as float2 arrays in INTERNAL order) so that a host
  * layer (torch.distributed / NCCL or CUDA IPC) can move halo particles without a host round trip. */
 int bendy_get_device_buffers(bendy_solver *s, void **pos, void **prev, size_t *n_points);

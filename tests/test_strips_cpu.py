@@ -1,0 +1,109 @@
+"""CPU tests of the strip sharding logic (no GPU): partition invariants, and a 2-process gloo run
+that moves the halo bands between ranks and checks that every contact partner is visible."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from bendy2d_b200 import scenes, strips
+
+f32 = np.float32
+
+
+def small_field():
+    sc = scenes.c3_softbody_field(8, 3, 0, 0)
+    # squeeze the columns together so that neighbouring bodies really touch across strip edges
+    col = (np.arange(sc.n_particles) // 500) % 8
+    sc.particles[:, 0] -= (col * 3.1).astype(f32)
+    return sc
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_partition_invariants(world):
+    sc = small_field()
+    parts = strips.partition_scene(sc, world)
+    owned = np.concatenate([p.global_index for p in parts])
+    assert sorted(owned.tolist()) == list(range(sc.n_particles)), "every particle owned exactly once"
+    assert sum(p.scene.n_links for p in parts) == sc.n_links
+    for p in parts:
+        ab = p.scene.links_ab.astype(np.int64)
+        assert (ab[:, 0] < ab[:, 1]).all() and ab.max() < p.scene.n_particles
+        g = p.global_index[ab]
+        d = sc.particles[g[:, 0]] - sc.particles[g[:, 1]]
+        np.testing.assert_allclose(np.hypot(d[:, 0], d[:, 1]), p.scene.links_len, rtol=1e-6)
+        assert p.x_left < p.x_right
+        if world > 1:
+            assert p.ghost_cap == parts[0].ghost_cap > 0
+    for a, b in zip(parts[:-1], parts[1:]):
+        assert a.x_right == b.x_left
+    assert parts[0].x_left == -np.inf and parts[-1].x_right == np.inf
+    # the automatic body detection agrees with the generator's body ids
+    assert len(np.unique(strips.body_ids(sc))) == len(np.unique(sc.body_of))
+
+
+def test_partition_rejects_circles():
+    sc = scenes.c3_softbody_field(2, 1, 2, 0)
+    with pytest.raises(ValueError):
+        strips.partition_scene(sc, 2)
+
+
+def _halo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = small_field()
+    part = strips.partition_scene(sc, world)[rank]
+    px = part.scene.particles
+    cap = part.ghost_cap
+    ghosts = []
+    reqs, bufs = [], []
+    for side, peer, mask in ((0, rank - 1, px[:, 0] < part.send_left_below),
+                             (1, rank + 1, px[:, 0] > part.send_right_above)):
+        if not 0 <= peer < world:
+            continue
+        send = torch.full((cap, 2), float("nan"))
+        sel = torch.from_numpy(px[mask])
+        assert len(sel) <= cap
+        send[: len(sel)] = sel
+        recv = torch.empty((cap, 2))
+        reqs += [dist.isend(send, peer), dist.irecv(recv, peer)]
+        bufs.append(recv)
+    for r in reqs:
+        r.wait()
+    for b in bufs:
+        g = b.numpy()
+        ghosts.append(g[np.isfinite(g[:, 0])])
+    local = np.concatenate([px] + ghosts) if ghosts else px
+    # every particle of the full scene within contact range of an owned particle must be local
+    r2 = (2 * sc.particle_radius + 1e-4) ** 2
+    full = sc.particles
+    missing = 0
+    for i in range(0, len(px), 997):  # sample owned particles
+        d2 = ((full - px[i]) ** 2).sum(1)
+        for j in np.nonzero(d2 < r2)[0]:
+            if not (np.abs(local - full[j]).sum(1) == 0).any():
+                missing += 1
+    q.put((rank, missing, sum(len(g) for g in ghosts)))
+    dist.destroy_process_group()
+
+
+def test_halo_bands_cover_all_contacts_gloo_world2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_halo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, missing, n_ghost in res:
+        assert missing == 0, f"rank {rank}: {missing} contact partners not covered by the halo"
+        assert n_ghost > 0
