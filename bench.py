@@ -257,6 +257,8 @@ def main():
         total_ms += solver.timer_stop()
     barrier()
     wall = time.perf_counter() - wall0
+    if world > 1:
+        solver.check_halo()  # overflow / stale ownership would make the run invalid: raise
     clocks = sampler.stop() if rank == 0 else None
     gpu_launches = solver.launch_count() - launches0
     if dist is not None:

@@ -99,12 +99,12 @@ def signatures():
         "bendy_get_stream": (vp, [vp]),
         "bendy_get_device": (i, [vp]),
         "bendy_get_device_buffers": (i, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]),
-        "bendy_halo_configure": (i, [vp, u32, fl, fl]),
+        "bendy_halo_configure": (i, [vp, u32, fl, fl, fl, fl]),
         "bendy_nccl_unique_id": (i, [vp]),
         "bendy_halo_comm_nccl": (i, [vp, vp, i, i]),
         "bendy_halo_connect_local": (i, [vp, vp]),
         "bendy_update_group": (i, [C.POINTER(vp), i, u32, fl, fl, fl, fl, fl, fl, fl]),
-        "bendy_halo_stats": (i, [vp, u32p, u32p, u32p]),
+        "bendy_halo_stats": (i, [vp, u32p, u32p, u32p, u32p]),
         "bendy_plan_links": (i, [sz, u32p, sz, u32, u32, u32p, u32p, u32p, u32p, C.POINTER(ScheduleInfo)]),
     }
     return _SIGS

@@ -185,7 +185,7 @@ struct bendy_solver {
     uint32_t ghost_cap = 0;   // ghost slots per side; discs [nOwned, nOwned+cap) come from the left neighbour,
                               // [nOwned+cap, nOwned+2cap) from the right one
     bool halo_on = false;
-    float halo_xl = -INFINITY, halo_xr = INFINITY;
+    float halo_xl = -INFINITY, halo_xr = INFINITY, stray_xl = -INFINITY, stray_xr = INFINITY;
     DevBuf<float2> d_send[2];
     DevBuf<uint32_t> d_send_cnt;
     ncclComm_t nccl_comm = nullptr;
@@ -522,8 +522,8 @@ int Ops::rebuild() {
     }
     if (s->halo_on && s->ghost_cap) {
         for (int side = 0; side < 2; side++) CK(s->d_send[side].ensure(s->ghost_cap));
-        CK(s->d_send_cnt.ensure(4));
-        CK(cudaMemsetAsync(s->d_send_cnt.p, 0, 4 * sizeof(uint32_t), s->stream));
+        CK(s->d_send_cnt.ensure(8));
+        CK(cudaMemsetAsync(s->d_send_cnt.p, 0, 8 * sizeof(uint32_t), s->stream));
         k_halo_clear<<<cdiv(s->ghost_cap, 256), 256, 0, s->stream>>>(s->d_send[0].p, s->d_send[1].p, s->d_send_cnt.p,
                                                                      s->ghost_cap);
         CK(cudaGetLastError());
@@ -583,6 +583,8 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
     p.rp = s->particle_radius;
     p.halo_xl = s->halo_on ? s->halo_xl : -INFINITY;
     p.halo_xr = s->halo_on ? s->halo_xr : INFINITY;
+    p.stray_xl = s->halo_on ? s->stray_xl : -INFINITY;
+    p.stray_xr = s->halo_on ? s->stray_xr : INFINITY;
     uint32_t ncells = 0;
     const bool discs = s->particle_radius > 0.f && s->nP > 0;
     if (discs) {
@@ -1555,7 +1557,8 @@ int bendy_get_device_buffers(bendy_solver *s, void **pos, void **prev, size_t *n
 }
 
 // ---- spatial strips: halo exchange ----------------------------------------------------------------
-int bendy_halo_configure(bendy_solver *s, uint32_t ghost_cap, float x_left, float x_right) {
+int bendy_halo_configure(bendy_solver *s, uint32_t ghost_cap, float x_left, float x_right, float stray_left,
+                         float stray_right) {
     NEED(s);
     OPS;
     if (ghost_cap > 0x3FFFFFFFu) return ops.fail(BENDY_ERR_ARG, "ghost capacity too large");
@@ -1563,6 +1566,7 @@ int bendy_halo_configure(bendy_solver *s, uint32_t ghost_cap, float x_left, floa
     s->halo_on = ghost_cap > 0;
     s->ghost_cap = ghost_cap;
     s->halo_xl = x_left, s->halo_xr = x_right;
+    s->stray_xl = stray_left, s->stray_xr = stray_right;
     s->prm_valid = false;
     edit_end(s);
     return BENDY_OK;
@@ -1614,18 +1618,20 @@ int bendy_halo_connect_local(bendy_solver *left, bendy_solver *right) {
     return BENDY_OK;
 }
 
-int bendy_halo_stats(bendy_solver *s, uint32_t *sent_left, uint32_t *sent_right, uint32_t *overflow) {
+int bendy_halo_stats(bendy_solver *s, uint32_t *sent_left, uint32_t *sent_right, uint32_t *overflow,
+                     uint32_t *strayed) {
     NEED(s);
     OPS;
-    uint32_t h[4] = {0, 0, 0, 0};
+    uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (s->d_send_cnt.p) {
         if (int rc = ops.bind()) return rc;
         CK(cudaStreamSynchronize(s->stream));
         CK(cudaMemcpy(h, s->d_send_cnt.p, sizeof h, cudaMemcpyDeviceToHost));
     }
-    if (sent_left) *sent_left = h[0];
-    if (sent_right) *sent_right = h[1];
+    if (sent_left) *sent_left = h[4];
+    if (sent_right) *sent_right = h[5];
     if (overflow) *overflow = h[2];
+    if (strayed) *strayed = h[3];
     return BENDY_OK;
 }
 

@@ -60,6 +60,16 @@ class StripPart:
     def send_right_above(self) -> float:
         return float(self.x_right - self.band) if np.isfinite(self.x_right) else float("inf")
 
+    # an owned disc further than band/2 inside a neighbour's strip makes the ownership stale: as long
+    # as nothing moves more than band/2 - 2r between two checks, no contact can have been missed
+    @property
+    def stray_left(self) -> float:
+        return float(self.x_left - 0.5 * self.band) if np.isfinite(self.x_left) else float("-inf")
+
+    @property
+    def stray_right(self) -> float:
+        return float(self.x_right + 0.5 * self.band) if np.isfinite(self.x_right) else float("inf")
+
 
 def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodies: Optional[np.ndarray] = None,
                     cap_factor: float = 2.0) -> List[StripPart]:
@@ -91,9 +101,10 @@ def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodi
             edges.append(0.5 * (a + b))
     edges.append(np.inf)
     if band is None:
-        # a body reaches half its width past the edge it was assigned by; + drift allowance + contact range
+        # a body reaches half its width past the edge it was assigned by; x2 because a disc may stray
+        # band/2 before the ownership is rebalanced; + drift allowance + contact range
         half = 0.5 * float(np.max(xmax - xmin)) if nb else 0.0
-        band = half + 1.0 + 2.0 * scene.particle_radius
+        band = 2.0 * half + 2.0 + 2.0 * scene.particle_radius
     strip_of_particle = strip_of_body[bodies]
     parts = []
     link_strip = strip_of_particle[scene.links_ab[:, 0].astype(np.int64)] if scene.n_links else np.zeros(0, np.int64)
@@ -126,8 +137,19 @@ def _load_part(part: StripPart, device: int) -> Solver:
     sv = Solver(device)
     part.scene.load_into(sv)
     if part.world > 1:
-        sv._ck(sv._L.bendy_halo_configure(sv._h, part.ghost_cap, part.send_left_below, part.send_right_above))
+        sv._ck(sv._L.bendy_halo_configure(sv._h, part.ghost_cap, part.send_left_below, part.send_right_above,
+                                          part.stray_left, part.stray_right))
     return sv
+
+
+def _halo_stats(sv: Solver):
+    a, b, o, st = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    sv._ck(sv._L.bendy_halo_stats(sv._h, C.byref(a), C.byref(b), C.byref(o), C.byref(st)))
+    return a.value, b.value, o.value, st.value
+
+
+class HaloError(RuntimeError):
+    pass
 
 
 class _StripBase:
@@ -139,11 +161,9 @@ class _StripBase:
     def local_scene(self) -> Scene:
         return self.part.scene
 
-    def halo_stats(self, sv: Optional[Solver] = None):
-        sv = sv or self.solver
-        a, b, o = C.c_uint32(), C.c_uint32(), C.c_uint32()
-        sv._ck(sv._L.bendy_halo_stats(sv._h, C.byref(a), C.byref(b), C.byref(o)))
-        return a.value, b.value, o.value
+    def halo_stats(self):
+        """(sent_left, sent_right, overflow, strayed) of the last substep"""
+        return _halo_stats(self.solver)
 
 
 class StripSolver(_StripBase):
@@ -151,11 +171,20 @@ class StripSolver(_StripBase):
 
     def __init__(self, scene: Scene, rank: int, world: int, device: int, dist=None, band: Optional[float] = None,
                  bodies: Optional[np.ndarray] = None):
+        self.rank, self.world, self.dist, self.device_index = rank, world, dist, device
+        self.full_scene, self.band = scene, band
+        self.bodies = bodies if bodies is not None else scene.body_of
+        self._uid = None
+        self._build(scene, None)
+
+    def _build(self, scene: Scene, prev: Optional[np.ndarray]):
         import torch
 
-        self.rank, self.world, self.dist = rank, world, dist
-        self.part = partition_scene(scene, world, band, bodies)[rank]
+        rank, world, dist, device = self.rank, self.world, self.dist, self.device_index
+        self.part = partition_scene(scene, world, self.band, self.bodies)[rank]
         self.solver = _load_part(self.part, device)
+        if prev is not None:
+            self.solver.write_particles(prev_xy=prev[self.part.global_index])
         if world > 1:
             L = self.solver._L
             uid = torch.zeros(128, dtype=torch.uint8)
@@ -177,10 +206,49 @@ class StripSolver(_StripBase):
         return getattr(self.solver, name)
 
     def check_halo(self):
-        l, r, o = self.halo_stats()
+        """Raises if the halo of this rank was invalid at any substep since the last check."""
+        l, r, o, st = self.halo_stats()
         if o:
-            raise RuntimeError(f"halo overflow on rank {self.rank}: ghost_cap {self.part.ghost_cap}, sent {l}/{r}")
+            raise HaloError(f"halo overflow on rank {self.rank}: ghost_cap {self.part.ghost_cap}, sent {l}/{r}")
+        if st:
+            raise HaloError(f"rank {self.rank}: an owned disc strayed more than band/2 = {0.5 * self.part.band:.3f} "
+                            "into a neighbour's strip; call rebalance() more often")
         return l, r
+
+    def needs_rebalance(self) -> bool:
+        import torch
+
+        flag = torch.tensor([1 if self.halo_stats()[3] else 0], device=f"cuda:{self.device_index}")
+        if self.world > 1:
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX)
+        return bool(flag.item())
+
+    def rebalance(self):
+        """Re-partition by the CURRENT positions: every rank gathers the full state (rare, host side),
+        cuts new strips of equal body count and rebuilds its local solver; pos and prev travel
+        bit-exactly, so the trajectory is unchanged."""
+        import torch
+
+        n = self.full_scene.n_particles
+        pos, prev = self.solver.read_particles()
+        dev = f"cuda:{self.device_index}"
+        cnt = torch.tensor([len(pos)], device=dev)
+        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        self.dist.all_gather(cnts, cnt)
+        m = int(max(c.item() for c in cnts))
+        pack = torch.zeros((m, 5), dtype=torch.float64, device=dev)
+        pack[: len(pos), 0] = torch.from_numpy(self.part.global_index.astype(np.float64)).to(dev)
+        pack[: len(pos), 1:3] = torch.from_numpy(pos.astype(np.float64)).to(dev)
+        pack[: len(pos), 3:5] = torch.from_numpy(prev.astype(np.float64)).to(dev)
+        packs = [torch.zeros_like(pack) for _ in range(self.world)]
+        self.dist.all_gather(packs, pack)
+        gpos, gprev = np.empty((n, 2), f32), np.empty((n, 2), f32)
+        for c, pk in zip(cnts, packs):
+            a = pk[: int(c.item())].cpu().numpy()
+            idx = a[:, 0].astype(np.int64)
+            gpos[idx], gprev[idx] = a[:, 1:3].astype(f32), a[:, 3:5].astype(f32)
+        self.solver = None
+        self._build(replace(self.full_scene, particles=gpos), gprev)
 
 
 class LocalStripGroup:
@@ -189,9 +257,16 @@ class LocalStripGroup:
 
     def __init__(self, scene: Scene, n_strips: int, device: int = -1, band: Optional[float] = None,
                  bodies: Optional[np.ndarray] = None):
-        self.scene = scene
-        self.parts = partition_scene(scene, n_strips, band, bodies)
-        self.solvers = [_load_part(p, device) for p in self.parts]
+        self.scene, self.n_strips, self.device, self.band = scene, n_strips, device, band
+        self.bodies = bodies if bodies is not None else scene.body_of
+        self._build(scene, None)
+
+    def _build(self, scene: Scene, prev: Optional[np.ndarray]):
+        self.parts = partition_scene(scene, self.n_strips, self.band, self.bodies)
+        self.solvers = [_load_part(p, self.device) for p in self.parts]
+        if prev is not None:
+            for p, s in zip(self.parts, self.solvers):
+                s.write_particles(prev_xy=prev[p.global_index])
         L = self.solvers[0]._L
         for a, b in zip(self.solvers[:-1], self.solvers[1:]):
             if L.bendy_halo_connect_local(a._h, b._h) != 0:
@@ -216,9 +291,13 @@ class LocalStripGroup:
         return pos, prev
 
     def halo_stats(self):
-        out = []
-        for s in self.solvers:
-            a, b, o = C.c_uint32(), C.c_uint32(), C.c_uint32()
-            s._ck(s._L.bendy_halo_stats(s._h, C.byref(a), C.byref(b), C.byref(o)))
-            out.append((a.value, b.value, o.value))
-        return out
+        return [_halo_stats(s) for s in self.solvers]
+
+    def needs_rebalance(self) -> bool:
+        return any(st for _, _, _, st in self.halo_stats())
+
+    def rebalance(self):
+        pos, prev = self.read_particles()
+        g, b = self.solvers[0].gravity, self.solvers[0].bounds
+        self.solvers = []
+        self._build(replace(self.scene, particles=pos), prev)

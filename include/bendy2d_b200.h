@@ -168,9 +168,12 @@ int bendy_get_device(const bendy_solver *s);
  * edges moved inwards by the halo band) are packed on the device and sent to the left / right
  * neighbour, where they occupy read-only ghost slots of the broadphase grid.  No reference
  * counterpart: the reference is single-threaded (solver.rs:109-188). */
-/* ghost_cap = ghost disc slots per side (0 turns strips off); x_left/x_right = -inf/+inf when there is
- * no neighbour on that side */
-int bendy_halo_configure(bendy_solver *s, uint32_t ghost_cap, float x_left, float x_right);
+/* ghost_cap = ghost disc slots per side (0 turns strips off); owned discs with x < x_left go to the
+ * left neighbour, x > x_right to the right one (-inf/+inf when there is no neighbour on that side);
+ * an owned disc outside [stray_left, stray_right] raises the `strayed` flag of bendy_halo_stats: it
+ * is so deep in a neighbour's strip that ownership has to be rebalanced by the host layer */
+int bendy_halo_configure(bendy_solver *s, uint32_t ghost_cap, float x_left, float x_right, float stray_left,
+                         float stray_right);
 /* rank 0 creates the NCCL id (128 bytes); the host layer (torch.distributed) broadcasts it */
 int bendy_nccl_unique_id(void *out128);
 /* joins the strip communicator: neighbours are rank-1 and rank+1; send/recv run on the solver's stream
@@ -181,8 +184,10 @@ int bendy_halo_connect_local(bendy_solver *left, bendy_solver *right);
 /* lock-step update of several same-process strips (phase A | halo copy | phase B per substep) */
 int bendy_update_group(bendy_solver **group, int n, uint32_t n_updates, float dt, float gx, float gy, float bx,
                        float by, float bw, float bh);
-/* discs packed for each neighbour in the last substep; overflow != 0 means ghost_cap was too small */
-int bendy_halo_stats(bendy_solver *s, uint32_t *sent_left, uint32_t *sent_right, uint32_t *overflow);
+/* discs packed for each neighbour in the last substep; overflow != 0 means ghost_cap was too small;
+ * strayed != 0 means ownership is stale (see bendy_halo_configure) */
+int bendy_halo_stats(bendy_solver *s, uint32_t *sent_left, uint32_t *sent_right, uint32_t *overflow,
+                     uint32_t *strayed);
 
 /* Device pointers of the internal SoA (pos, prev as float2 arrays in INTERNAL order) so that a host
  * layer (torch.distributed / NCCL or CUDA IPC) can move halo particles without a host round trip. */

@@ -37,8 +37,8 @@ def test_local_strip_group_is_bit_identical_to_single_solver(n_strips):
         gp, gq = grp.read_particles()
         assert max_ulp(gp, rp) == 0 and max_ulp(gq, rq) == 0, f"after {10 * (k + 1)} substeps"
     stats = grp.halo_stats()
-    assert all(o == 0 for _, _, o in stats), stats
-    assert sum(a + b for a, b, _ in stats) > 0, "no halo traffic: the test scene does not exercise the exchange"
+    assert all(o == 0 and st == 0 for _, _, o, st in stats), stats
+    assert sum(a + b for a, b, _, _ in stats) > 0, "no halo traffic: the test scene does not exercise the exchange"
     # contacts across strip edges really happened: positions differ from a run without collisions
     free = Solver()
     sc2 = touching_field()
@@ -48,16 +48,35 @@ def test_local_strip_group_is_bit_identical_to_single_solver(n_strips):
     assert not np.array_equal(bits(free.read_particles()[0]), bits(rp))
 
 
-def test_strip_group_with_sub_steps_and_c2_free_particles():
+def test_strip_group_free_particles_with_rebalancing():
+    """Free particles pile up and spread sideways, so ownership has to follow the positions: the
+    stray flag is polled every update (max speed ~45 units/s = 0.4 per substep << band/2)."""
     sc = scenes.c2_free_particles(80, 30)
     sc.bounds = (0.0, 0.0, 48.0, 12.0)
-    sc.sub_steps = 4
-    sc.dt = 4.0 / 120.0
     ref = Solver()
     sc.load_into(ref)
-    grp = strips.LocalStripGroup(sc, 4, band=1.5)
-    ref.update(sc.dt, n=25)
-    grp.update(sc.dt, n=25)
+    grp = strips.LocalStripGroup(sc, 4, band=4.0)
+    rebalanced = 0
+    for _ in range(150):
+        ref.update(sc.dt)
+        grp.update(sc.dt)
+        if grp.needs_rebalance():
+            grp.rebalance()
+            rebalanced += 1
+    assert all(o == 0 for _, _, o, _ in grp.halo_stats())
+    gp, gq = grp.read_particles()
+    rp, rq = ref.read_particles()
+    assert max_ulp(gp, rp) == 0 and max_ulp(gq, rq) == 0, f"rebalanced {rebalanced} times"
+
+
+def test_strip_group_sub_steps():
+    sc = touching_field(6, 2)
+    sc.sub_steps, sc.dt = 4, 4.0 / 120.0
+    ref = Solver()
+    sc.load_into(ref)
+    grp = strips.LocalStripGroup(sc, 3)
+    ref.update(sc.dt, n=10)
+    grp.update(sc.dt, n=10)
     assert max_ulp(grp.read_particles()[0], ref.read_particles()[0]) == 0
 
 
