@@ -186,6 +186,7 @@ struct bendy_solver {
                               // [nOwned+cap, nOwned+2cap) from the right one
     bool halo_on = false;
     float halo_xl = -INFINITY, halo_xr = INFINITY, stray_xl = -INFINITY, stray_xr = INFINITY;
+    float win_x0 = -INFINITY, win_x1 = INFINITY;  // x-range the broadphase grid covers (clipped to the bounds)
     DevBuf<float2> d_send[2];
     DevBuf<uint32_t> d_send_cnt;
     ncclComm_t nccl_comm = nullptr;
@@ -549,6 +550,13 @@ int Ops::ensure_ready() {
 // broadphase grid for these bounds: origin = bounds.pos, h >= 2*r_p, cell count bounded
 int Ops::grid_for(float bx, float by, float bw, float bh, StepParams *p, uint32_t *ncells) {
     double wx = std::isfinite(bw) && bw > 0.f ? bw : 1.0, wy = std::isfinite(bh) && bh > 0.f ? bh : 1.0;
+    // a strip only needs cells where its own discs and ghosts can be: clip the grid to the window
+    // (discs outside are clamped into the border cells, which stays correct)
+    if (s->win_x0 > bx && s->win_x0 < bx + (float)wx) {
+        wx -= (double)(s->win_x0 - bx);
+        bx = s->win_x0;
+    }
+    if (s->win_x1 > bx && s->win_x1 < bx + (float)wx) wx = (double)(s->win_x1 - bx);
     float h = s->grid_cell;
     if (!(h > 0.f)) {
         // auto: about two cells per particle (the per-cell scan traffic then stays below the per-disc
@@ -1557,6 +1565,16 @@ int bendy_get_device_buffers(bendy_solver *s, void **pos, void **prev, size_t *n
 }
 
 // ---- spatial strips: halo exchange ----------------------------------------------------------------
+int bendy_set_grid_window(bendy_solver *s, float x0, float x1) {
+    NEED(s);
+    OPS;
+    if (!(x0 < x1)) return ops.fail(BENDY_ERR_ARG, "bendy_set_grid_window: need x0 < x1");
+    s->win_x0 = x0, s->win_x1 = x1;
+    s->prm_valid = false;
+    ops.drop_graph();
+    return BENDY_OK;
+}
+
 int bendy_halo_configure(bendy_solver *s, uint32_t ghost_cap, float x_left, float x_right, float stray_left,
                          float stray_right) {
     NEED(s);

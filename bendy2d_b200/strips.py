@@ -139,6 +139,10 @@ def _load_part(part: StripPart, device: int) -> Solver:
     if part.world > 1:
         sv._ck(sv._L.bendy_halo_configure(sv._h, part.ghost_cap, part.send_left_below, part.send_right_above,
                                           part.stray_left, part.stray_right))
+        # cells only where owned discs (up to the stray limit) and ghosts (one band beyond the edge) can be
+        x0 = part.x_left - 1.5 * part.band if np.isfinite(part.x_left) else -3.0e38
+        x1 = part.x_right + 1.5 * part.band if np.isfinite(part.x_right) else 3.0e38
+        sv._ck(sv._L.bendy_set_grid_window(sv._h, x0, x1))
     return sv
 
 

@@ -174,6 +174,9 @@ int bendy_get_device(const bendy_solver *s);
  * is so deep in a neighbour's strip that ownership has to be rebalanced by the host layer */
 int bendy_halo_configure(bendy_solver *s, uint32_t ghost_cap, float x_left, float x_right, float stray_left,
                          float stray_right);
+/* restricts the broadphase grid to x in [x0, x1] (clipped to the bounds): a strip needs cells only
+ * for its own discs and ghosts.  Results do not depend on it (the grid only prunes pairs). */
+int bendy_set_grid_window(bendy_solver *s, float x0, float x1);
 /* rank 0 creates the NCCL id (128 bytes); the host layer (torch.distributed) broadcasts it */
 int bendy_nccl_unique_id(void *out128);
 /* joins the strip communicator: neighbours are rank-1 and rank+1; send/recv run on the solver's stream
