@@ -149,15 +149,15 @@ struct bendy_solver {
     bool topo_dirty = true;     // plan / device tables must be rebuilt
 
     // ---------------- plan + device tables
-    LinkPlan plan_p, plan_g;
+    LinkPlan plan_p;
     uint32_t nP = 0, nC = 0, nG = 0, N = 0, Npad = 0;
     DevBuf<float2> d_pos, d_prev, d_accel, d_stage;
     DevBuf<float> d_k, d_crad;
     DevBuf<uint8_t> d_gstatic;
     DevBuf<uint32_t> d_rank;  // user particle -> internal
-    DevBuf<uint32_t> d_part_start, d_part_cs, d_gpart_start, d_gpart_cs;
-    DevBuf<LocalLink> d_local, d_glocal;
-    DevBuf<GlobalLink> d_global, d_gglobal, d_clinks;
+    DevBuf<uint32_t> d_part_start, d_part_cs;
+    DevBuf<LocalLink> d_local;
+    DevBuf<GlobalLink> d_global, d_clinks;
     bool accel_pending = false;
     bool has_k = false;
     // grid
@@ -175,6 +175,8 @@ struct bendy_solver {
     DevBuf<uint32_t> d_poly_start, d_poly_tiles;
     DevBuf<uint8_t> d_poly_static;
     DevBuf<float2> d_poly_center;
+    DevBuf<uint32_t> d_poly_first_row, d_poly_link_start, d_poly_link_ab;
+    DevBuf<float> d_poly_link_len;
     DevBuf<float4> d_poly_box;
     float poly_tile = 0.f;
     uint32_t n_poly_tiles = 0;
@@ -421,19 +423,6 @@ int Ops::rebuild() {
     if (!plan_links(s->nOwned, s->pl_ab.data(), s->pl_len.data(), s->pl_len.size(), s->plan_params, false, &s->plan_p,
                     &perr))
         return fail(BENDY_ERR_UNSUPPORTED, perr);
-    // polygon-internal links (polygon.rs:218-223) use polygon-local indices: rebase to the polygon
-    // point array; the order of polygon points is part of the shape, so keep_order = true
-    {
-        std::vector<uint32_t> ab(s->gl_ab.size());
-        for (const PolyHost &P : s->polys)
-            for (uint32_t k = 0; k < P.nl; k++) {
-                ab[2 * (P.link_start + k)] = s->gl_ab[2 * (P.link_start + k)] + P.start;
-                ab[2 * (P.link_start + k) + 1] = s->gl_ab[2 * (P.link_start + k) + 1] + P.start;
-            }
-        if (!plan_links(s->nG, ab.data(), s->gl_len.data(), s->gl_len.size(), s->plan_params, true, &s->plan_g,
-                        &perr))
-            return fail(BENDY_ERR_UNSUPPORTED, perr);
-    }
     // ---- state upload (internal order)
     std::vector<float2> pos(s->Npad), prev(s->Npad);
     for (uint32_t i = 0; i < s->nOwned; i++) {
@@ -472,10 +461,13 @@ int Ops::rebuild() {
     CK(upload(s->d_part_cs, s->plan_p.part_colour_start, s->stream));
     CK(upload(s->d_local, s->plan_p.local_links, s->stream));
     CK(upload(s->d_global, s->plan_p.global_links, s->stream));
-    CK(upload(s->d_gpart_start, s->plan_g.part_start, s->stream));
-    CK(upload(s->d_gpart_cs, s->plan_g.part_colour_start, s->stream));
-    CK(upload(s->d_glocal, s->plan_g.local_links, s->stream));
-    CK(upload(s->d_gglobal, s->plan_g.global_links, s->stream));
+    {  // polygon-internal links stay in insertion order with polygon-local indices (polygon.rs:218-223)
+        std::vector<uint32_t> ls(s->polys.size() + 1, 0);
+        for (size_t k = 0; k < s->polys.size(); k++) ls[k] = s->polys[k].link_start, ls[k + 1] = s->polys[k].link_start + s->polys[k].nl;
+        CK(upload(s->d_poly_link_start, ls, s->stream));
+        CK(upload(s->d_poly_link_ab, s->gl_ab, s->stream));
+        CK(upload(s->d_poly_link_len, s->gl_len, s->stream));
+    }
     CK(upload(s->d_clinks, s->cl, s->stream));
     // ---- polygons
     {
@@ -504,6 +496,8 @@ int Ops::rebuild() {
         CK(upload(s->d_gstatic, gstatic, s->stream));
         CK(upload(s->d_poly_center, cen, s->stream));
         CK(s->d_poly_box.ensure(std::max<size_t>(s->polys.size(), 1)));
+        CK(s->d_poly_first_row.ensure(1));
+        CK(cudaMemsetAsync(s->d_poly_first_row.p, 0xFF, sizeof(uint32_t), s->stream));
     }
     if (!s->d_flags.p) {
         CK(s->d_flags.ensure(1));
@@ -601,8 +595,9 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
         p.nx = p.ny = p.tnx = p.tny = 1, p.gox = bx, p.goy = by, p.h = 1.f, p.inv_h = 1.f, p.quad = 0;
     }
     const bool contact = s->polygon_contact && !s->polys.empty() && s->nP > 0;
+    const bool poly_tiles = contact || s->polys.size() >= 2;  // also the polygon-polygon pre-scan bins
     uint32_t ptiles = 0;
-    if (contact) {
+    if (poly_tiles) {
         float t = s->poly_tile;
         double wx = std::isfinite(bw) && bw > 0.f ? bw : 1.0, wy = std::isfinite(bh) && bh > 0.f ? bh : 1.0;
         while (std::ceil(wx / t) * std::ceil(wy / t) > 4194304.0) t *= 1.25f;
@@ -646,7 +641,7 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
                 CK(s->d_circ_tile_ids.ensure((size_t)s->n_circ_tiles * BENDY_CIRC_CAP));
             }
         }
-        if (contact) {
+        if (poly_tiles) {
             s->n_poly_tiles = ptiles;
             CK(s->d_poly_tiles.ensure((size_t)ptiles * (BENDY_POLY_CAP + 1)));
         }
@@ -764,16 +759,22 @@ int Ops::launch_substep(int phase) {
     cudaStream_t qc = (branch && s->nC > 0) ? s->side[0] : st;
     cudaStream_t qg = (branch && nPoly > 0) ? s->side[1] : st;
     PolyArgs pa{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_static.p, nPoly, s->d_poly_center.p,
-                s->d_poly_box.p,     s->d_poly_tiles.p, s->d_flags.p};
+                s->d_poly_box.p,     s->d_poly_tiles.p, s->d_flags.p, s->d_poly_first_row.p};
     if (poly_work) {
         LAUNCH(BENDY_K_POLY_PREP, k4_poly_center<<<cdiv(nPoly, 128), 128, 0, qg>>>(pa));
-        if (int rc = run_plan(s->plan_g, s->nP + s->nC, s->d_gpart_start.p, s->d_gpart_cs.p, s->d_glocal.p,
-                              s->d_gglobal.p, qg, false))
-            return rc;
-        if (contact) {
+        if (!s->gl_len.empty())
+            LAUNCH(BENDY_K_LINKS_LOCAL, k3_polygon_links<<<cdiv(nPoly, 128), 128, 0, qg>>>(
+                                            pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_link_start.p,
+                                            s->d_poly_link_ab.p, s->d_poly_link_len.p, nPoly));
+        if (contact || nPoly >= 2) {
             LAUNCH(BENDY_K_POLY_PREP, cudaMemsetAsync(s->d_poly_tiles.p, 0,
                                                       (size_t)s->n_poly_tiles * (BENDY_POLY_CAP + 1) * sizeof(uint32_t), qg));
             LAUNCH(BENDY_K_POLY_PREP, k4_poly_box_bin<<<cdiv(nPoly, 128), 128, 0, qg>>>(pa, prm));
+        }
+        if (nPoly >= 2) {  // solve_dynamic_collisions, polygon half (solver.rs:178-187)
+            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_pair_prescan<<<cdiv(nPoly, 128), 128, 0, qg>>>(pa, prm));
+            LAUNCH(BENDY_K_POLY_CONTACT,
+                   k_polygons_exact<<<1, 1024, 0, qg>>>(pos + s->nP + s->nC, pa, prm, s->n_poly_tiles));
         }
     }
     // ---- circle chain: circle links (solver.rs:147-149) -> circle-circle pass (solver.rs:168-177) -> bins
@@ -854,7 +855,8 @@ phase_b:
             CK(cudaStreamWaitEvent(st, s->ev_join[1], 0));
         }
     }
-    K4Args k4{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_center.p, s->d_poly_box.p, s->d_poly_tiles.p};
+    K4Args k4{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_center.p, s->d_poly_box.p, s->d_poly_tiles.p,
+              s->d_poly_static.p};
     K1Args k1{pos,         s->d_prev.p,    s->accel_pending ? s->d_accel.p : nullptr, dk,
               s->d_crad.p, s->d_gstatic.p, s->nP, s->nC, s->N};
     const bool acc = s->accel_pending;
@@ -1472,7 +1474,7 @@ int bendy_get_schedule_info(bendy_solver *s, bendy_schedule_info *out) {
     OPS;
     if (!out) return ops.fail(BENDY_ERR_ARG, "null out");
     if (int rc = ops.ensure_ready()) return rc;
-    fill_info(s->plan_p, &s->plan_g, out);
+    fill_info(s->plan_p, nullptr, out);
     out->kernels_per_substep = s->kernels_per_substep;
     return BENDY_OK;
 }

@@ -274,6 +274,61 @@ def test_polygons_links_center_static_semantics():
     assert g.get_polygon(1).is_static and not g.get_polygon(0).is_static
 
 
+def test_polygon_polygon_contact_kpoly1_and_reference_order():
+    """solve_polygon on the device (polygon.rs:142-216): the K-poly-1 pair, then a heap of polygons
+    falling onto each other; compared bit for bit with the oracle's literal all-pairs loop."""
+    g, o = Solver(), bo.OracleSolver()
+    g.gravity = np.zeros(2, f32)
+    o.set_gravity(0, 0)
+    A = np.array([[0, 0], [4, 0], [4, 4], [0, 4]], f32) + 20
+    B = np.array([[3, 1], [7, 1], [7, 3], [3, 3]], f32) + 20
+    for pts in (A, B):
+        g.add_polygon(Polygon.new(pts, False))
+        o.add_polygon_new(pts, False)
+    for k in range(5):
+        g.update(0.01)
+        o.update(0.01)
+        for idx in range(2):
+            pp, pq, pc, _ = g.read_polygon(idx)
+            op, oq, oc = o.polygon(idx)
+            assert max_ulp(pp, op) == 0 and max_ulp(pq, oq) == 0 and max_ulp(pc, oc) == 0, (k, idx)
+    moved = g.read_polygon(0)[0]
+    assert not np.array_equal(moved, A), "the pair did interact"
+
+
+def test_polygon_heap_falls_and_collides_bit_exact():
+    rng = np.random.default_rng(11)
+    g, o = Solver(), bo.OracleSolver()
+    g.bounds.size[:] = (40.0, 40.0)
+    o.set_bounds(0, 0, 40, 40)
+    polys = []
+    for k in range(14):
+        c = np.array([6.0 + 4.5 * (k % 6) + rng.uniform(-0.3, 0.3), 8.0 + 7.0 * (k // 6) + rng.uniform(-0.3, 0.3)])
+        nv = int(rng.integers(3, 7))
+        ang = rng.uniform(0, 6.28) + 2 * np.pi * np.arange(nv) / nv
+        pts = (c + rng.uniform(1.6, 2.6) * np.stack([np.cos(ang), np.sin(ang)], 1)).astype(f32)
+        static = k % 5 == 4
+        polys.append((pts, static))
+        g.add_polygon(Polygon.new(pts, static))
+        o.add_polygon_new(pts, static)
+    hits = False
+    for k in range(160):
+        g.update(1 / 120)
+        o.update(1 / 120)
+        if k % 8 == 7 or k == 159:
+            for idx in range(len(polys)):
+                pp, pq, pc, _ = g.read_polygon(idx)
+                op, oq, oc = o.polygon(idx)
+                assert max_ulp(pp, op) == 0 and max_ulp(pq, oq) == 0, (k, idx)
+    # the heap really collided: a copy without neighbours falls differently
+    solo = bo.OracleSolver()
+    solo.set_bounds(0, 0, 40, 40)
+    solo.add_polygon_new(polys[0][0], polys[0][1])
+    for _ in range(160):
+        solo.update(1 / 120)
+    assert not np.array_equal(solo.polygon(0)[0], o.polygon(0)[0])
+
+
 def test_pending_acc_on_circle_is_consumed_once():
     g, o = Solver(), bo.OracleSolver()
     c = Circle(Particle([50.0, 50.0]), 1.0)
