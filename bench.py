@@ -248,13 +248,15 @@ def main():
     barrier()
     wall0 = time.perf_counter()
     total_ms = 0.0
+    step_ms = []
     for _ in range(args.steps):
         flush_l2()
         if dist is not None:
             dist.barrier()
         solver.timer_start()
         solver.update(sc.dt)
-        total_ms += solver.timer_stop()
+        step_ms.append(solver.timer_stop())
+        total_ms += step_ms[-1]
     barrier()
     wall = time.perf_counter() - wall0
     if world > 1:
@@ -383,6 +385,7 @@ def main():
                    "l2": "warm between steps" if args.no_flush else "flushed between steps (256 MiB memset)",
                    "parallelism": f"strips{world}" if world > 1 else "single"},
         "value_warm_l2": value_warm, "wall_s_timed_region": wall,
+        "ms_per_step_series": [round(x, 4) for x in step_ms],
         "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "schedule": info,
     }

@@ -24,7 +24,7 @@ ERR_NAMES = {-1: "BENDY_ERR_ARG", -2: "BENDY_ERR_LINK", -3: "BENDY_ERR_CUDA", -4
              -5: "BENDY_ERR_NO_DEVICE"}
 
 K_CLASSES = ["integrate", "links_local", "links_global", "links_circle", "grid_build", "narrowphase", "circles",
-             "poly_prep", "poly_contact", "halo"]
+             "poly_prep", "poly_contact", "halo", "circle_pass"]
 
 
 class ScheduleInfo(C.Structure):
@@ -93,6 +93,7 @@ def signatures():
         "bendy_get_grid": (i, [vp, fl, fl, fl, fl, f32p, f32p, f32p, intp, intp]),
         "bendy_set_profiling": (i, [vp, i]),
         "bendy_get_kernel_times": (i, [vp, f64p, u64p, i, i]),
+        "bendy_get_stats": (i, [vp, u64p, i]),
         "bendy_launch_count": (C.c_uint64, [vp]),
         "bendy_timer_start": (i, [vp]),
         "bendy_timer_stop": (i, [vp, f32p]),

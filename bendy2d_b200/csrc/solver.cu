@@ -500,8 +500,8 @@ int Ops::rebuild() {
         CK(cudaMemsetAsync(s->d_poly_first_row.p, 0xFF, sizeof(uint32_t), s->stream));
     }
     if (!s->d_flags.p) {
-        CK(s->d_flags.ensure(1));
-        CK(cudaMemsetAsync(s->d_flags.p, 0, sizeof(int), s->stream));
+        CK(s->d_flags.ensure(8));  // [0] error flags, [1..4] circle-pass fallbacks (statistics)
+        CK(cudaMemsetAsync(s->d_flags.p, 0, 8 * sizeof(int), s->stream));
     }
     CK(s->d_prm.ensure(1));
     if (!s->h_prm_ring) {
@@ -783,7 +783,8 @@ int Ops::launch_substep(int phase) {
                k3_circle_links<<<1, 32, 0, qc>>>(pos + s->nP, s->d_crad.p, s->d_clinks.p, (uint32_t)s->cl.size()));
     if (s->nC >= 2) {
         size_t smem = s->nC <= 4096 ? (size_t)s->nC * 12 : 0;
-        LAUNCH(BENDY_K_CIRCLES, k_circles_exact<<<1, 1024, smem, qc>>>(pos + s->nP, s->d_crad.p, s->nC, smem ? 1 : 0));
+        LAUNCH(BENDY_K_CIRCLE_PASS,
+               k_circles_exact<<<1, 1024, smem, qc>>>(pos + s->nP, s->d_crad.p, s->nC, smem ? 1 : 0, s->d_flags.p + 1));
     }
     if (discs && s->nC)
         LAUNCH(BENDY_K_CIRCLES, k2_circle_bin<<<cdiv(s->nC, 128), 128, 0, qc>>>(pos + s->nP, s->d_crad.p, s->nC, prm,
@@ -1534,6 +1535,20 @@ int bendy_get_kernel_times(bendy_solver *s, double *ms, uint64_t *launches, int 
     return BENDY_OK;
 }
 uint64_t bendy_launch_count(const bendy_solver *s) { return s ? s->launches : 0; }
+
+int bendy_get_stats(bendy_solver *s, uint64_t *out, int n) {
+    NEED(s);
+    OPS;
+    if (!out || n < 1) return ops.fail(BENDY_ERR_ARG, "bendy_get_stats: bad arguments");
+    for (int k = 0; k < n; k++) out[k] = 0;
+    if (!s->d_flags.p) return BENDY_OK;
+    if (int rc = ops.bind()) return rc;
+    int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpy(h, s->d_flags.p, sizeof h, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n && k < 4; k++) out[k] = (uint64_t)h[1 + k];  // total, path bound, list overflow, scale
+    return BENDY_OK;
+}
 
 int bendy_timer_start(bendy_solver *s) {
     NEED(s);

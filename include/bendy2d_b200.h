@@ -146,6 +146,7 @@ enum {
     BENDY_K_POLY_PREP,     /* polygon centre / AABB / binning */
     BENDY_K_POLY_CONTACT,  /* K4 particle-polygon closest edge (+ polygon-polygon) */
     BENDY_K_HALO,          /* strips: halo exchange (NCCL send/recv or peer copy) + send-buffer reset */
+    BENDY_K_CIRCLE_PASS,   /* exact circle-circle pass (solver.rs:168-177) */
     BENDY_K_CLASSES
 };
 /* profile != 0: launch kernels one by one with cudaEvent pairs (slower; for per-kernel timing).
@@ -153,6 +154,9 @@ enum {
 int bendy_set_profiling(bendy_solver *s, int profile);
 /* accumulated device ms and launch counts per kernel class since the last reset */
 int bendy_get_kernel_times(bendy_solver *s, double *ms, uint64_t *launches, int n_classes, int reset);
+/* diagnostic counters: out[0] = substeps in which the parallel exact circle pass had to fall back to
+ * the plain sequential pass (its path-length bound did not hold) */
+int bendy_get_stats(bendy_solver *s, uint64_t *out, int n);
 /* kernels launched (graph nodes included) since creation: the gpu_launches figure of bench.py */
 uint64_t bendy_launch_count(const bendy_solver *s);
 /* cudaEvent timer on the solver's stream */
