@@ -30,7 +30,7 @@ K_CLASSES = ["integrate", "links_local", "links_global", "links_circle", "grid_b
 class ScheduleInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "n_partitions", "n_local_colours", "n_global_colours", "n_local_links", "n_global_links",
-        "n_poly_partitions", "kernels_per_substep", "reserved")]
+        "n_poly_partitions", "kernels_per_substep", "n_priority_partitions")]
 
 
 def build(force: bool = False) -> str:

@@ -40,7 +40,7 @@ std::vector<uint32_t> LinkPlan::perm() const {
 }
 
 bool plan_links(size_t n_points, const uint32_t *ab, const float *len, size_t n_links, const PlanParams &pp_in,
-                bool keep_order, LinkPlan *out, std::string *err) {
+                bool keep_order, LinkPlan *out, std::string *err, const uint8_t *priority) {
     PlanParams pp = pp_in;
     if (pp.max_points == 0) pp.max_points = PlanParams().max_points;
     if (pp.pack_points == 0) pp.pack_points = PlanParams().pack_points;
@@ -56,6 +56,7 @@ bool plan_links(size_t n_points, const uint32_t *ab, const float *len, size_t n_
 
     // ---- 1. renumber: linked components first (by first appearance), unlinked points last
     size_t n_linked = 0;
+    size_t n_priority_points = 0;
     if (keep_order || n_links == 0) {
         std::iota(P.rank.begin(), P.rank.end(), 0u);
         std::iota(P.order.begin(), P.order.end(), 0u);
@@ -78,13 +79,23 @@ bool plan_links(size_t n_points, const uint32_t *ab, const float *len, size_t n_
         std::vector<uint32_t> comp_size(n, 0);
         for (uint32_t i = 0; i < n; i++)
             if (linked[i]) comp_size[uf_find(parent, i)]++;
+        // components holding a priority point (strips: bodies near a strip edge) are numbered first so
+        // that their partitions form the leading range [0, n_priority_parts)
+        std::vector<uint8_t> comp_prio(priority ? n : 0, 0);
+        if (priority)
+            for (uint32_t i = 0; i < n; i++)
+                if (linked[i] && priority[i]) comp_prio[uf_find(parent, i)] = 1;
         std::vector<uint32_t> comp_off(n, 0);
         uint32_t run = 0;
-        for (uint32_t r = 0; r < n; r++) {
-            if (comp_size[r]) {
+        for (int pass = priority ? 0 : 1; pass < 2; pass++) {
+            for (uint32_t r = 0; r < n; r++) {
+                if (!comp_size[r]) continue;
+                const bool prio = priority && comp_prio[r];
+                if (priority && prio != (pass == 0)) continue;
                 comp_off[r] = run;
                 run += comp_size[r];
             }
+            if (pass == 0) n_priority_points = run;
         }
         n_linked = run;
         uint32_t free_run = run;
@@ -110,7 +121,9 @@ bool plan_links(size_t n_points, const uint32_t *ab, const float *len, size_t n_
     P.part_start.push_back(0);
     size_t pos = 0;
     while (pos < n_linked) {
+        if (pos == n_priority_points) P.n_priority_parts = P.n_parts();
         size_t lim = std::min(n_linked, pos + (size_t)pp.max_points);
+        if (pos < n_priority_points) lim = std::min(lim, n_priority_points);  // never pack across the group edge
         size_t best = 0;
         for (size_t e = pos + 1; e <= lim; e++) {
             if (crossing[e] != 0) continue;
@@ -125,6 +138,7 @@ bool plan_links(size_t n_points, const uint32_t *ab, const float *len, size_t n_
         P.part_start.push_back((uint32_t)best);
         pos = best;
     }
+    if (n_priority_points >= n_linked) P.n_priority_parts = P.n_parts();
     const uint32_t n_parts = P.n_parts();
     std::vector<uint32_t> part_of(n_linked);
     for (uint32_t p = 0; p < n_parts; p++)

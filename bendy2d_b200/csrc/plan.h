@@ -44,6 +44,7 @@ struct LinkPlan {
     std::vector<uint32_t> gcolour_start;     // G+1 offsets into global_links
     std::vector<GlobalLink> global_links;
     std::vector<uint32_t> global_user;
+    uint32_t n_priority_parts = 0;           // leading partitions made of components with a priority point
     uint32_t n_parts() const { return part_start.empty() ? 0u : (uint32_t)part_start.size() - 1; }
     uint32_t n_global_colours() const { return gcolour_start.empty() ? 0u : (uint32_t)gcolour_start.size() - 1; }
     // sequential-equivalent order of user link indices
@@ -54,6 +55,6 @@ struct LinkPlan {
 // ranges cut at max_points (used for polygon points, whose order is part of the polygon's shape).
 // Returns false and sets err on failure (vertex degree too high for the colour masks).
 bool plan_links(size_t n_points, const uint32_t *ab, const float *len, size_t n_links, const PlanParams &pp,
-                bool keep_order, LinkPlan *out, std::string *err);
+                bool keep_order, LinkPlan *out, std::string *err, const uint8_t *priority = nullptr);
 
 }  // namespace bendy

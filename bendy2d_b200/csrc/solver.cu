@@ -260,7 +260,7 @@ struct Ops {  // helper with access to the solver; keeps bendy_solver a plain st
     int grid_for(float bx, float by, float bw, float bh, StepParams *p, uint32_t *ncells);
     int enqueue_substeps(uint32_t count);
     int launch_substep(int phase = PHASE_ALL);
-    int halo_exchange_nccl();
+    int halo_exchange_nccl(cudaStream_t q);
     int build_graph(uint32_t substeps);
     void drop_graph();
     int flush_events();
@@ -420,8 +420,19 @@ int Ops::rebuild() {
     s->N = s->nP + s->nC + s->nG;
     s->Npad = (s->N + 1u) & ~1u;
     std::string perr;
+    // strips: bodies close to a halo band are relaxed first so that the exchange can overlap the rest
+    std::vector<uint8_t> prio;
+    if (s->halo_on && s->ghost_cap) {
+        const float gl = std::isfinite(s->halo_xl) ? (s->halo_xl - s->stray_xl) / 3.0f : 0.f;  // = band / 2
+        const float gr = std::isfinite(s->halo_xr) ? (s->stray_xr - s->halo_xr) / 3.0f : 0.f;
+        prio.resize(s->nOwned);
+        for (uint32_t i = 0; i < s->nOwned; i++) {
+            const float x = s->p_pos[i].x;
+            prio[i] = (x < s->halo_xl + gl || x > s->halo_xr - gr || !(x == x)) ? 1 : 0;
+        }
+    }
     if (!plan_links(s->nOwned, s->pl_ab.data(), s->pl_len.data(), s->pl_len.size(), s->plan_params, false, &s->plan_p,
-                    &perr))
+                    &perr, prio.empty() ? nullptr : prio.data()))
         return fail(BENDY_ERR_UNSUPPORTED, perr);
     // ---- state upload (internal order)
     std::vector<float2> pos(s->Npad), prev(s->Npad);
@@ -668,7 +679,7 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
 // Free particles, circles and polygon points are disjoint worlds until the collision phase
 // (solver.rs:143-153), so while capturing a graph the circle and polygon chains run as parallel
 // branches beside the particle chain; eager (profiling) launches are simply serial.
-int Ops::halo_exchange_nccl() {
+int Ops::halo_exchange_nccl(cudaStream_t q) {
     if (!s->nccl_comm) return BENDY_OK;  // a single strip: nothing to exchange
     const size_t nflt = 2 * (size_t)s->ghost_cap;
     float2 *ghost = s->d_pos.p + s->nOwned;
@@ -680,12 +691,12 @@ int Ops::halo_exchange_nccl() {
     };
     if (int rc = ck(g_nccl.GroupStart(), "ncclGroupStart")) return rc;
     if (left >= 0) {
-        if (int rc = ck(g_nccl.Send(s->d_send[0].p, nflt, ncclFloat, left, s->nccl_comm, s->stream), "ncclSend")) return rc;
-        if (int rc = ck(g_nccl.Recv(ghost, nflt, ncclFloat, left, s->nccl_comm, s->stream), "ncclRecv")) return rc;
+        if (int rc = ck(g_nccl.Send(s->d_send[0].p, nflt, ncclFloat, left, s->nccl_comm, q), "ncclSend")) return rc;
+        if (int rc = ck(g_nccl.Recv(ghost, nflt, ncclFloat, left, s->nccl_comm, q), "ncclRecv")) return rc;
     }
     if (right < s->comm_world) {
-        if (int rc = ck(g_nccl.Send(s->d_send[1].p, nflt, ncclFloat, right, s->nccl_comm, s->stream), "ncclSend")) return rc;
-        if (int rc = ck(g_nccl.Recv(ghost + s->ghost_cap, nflt, ncclFloat, right, s->nccl_comm, s->stream), "ncclRecv"))
+        if (int rc = ck(g_nccl.Send(s->d_send[1].p, nflt, ncclFloat, right, s->nccl_comm, q), "ncclSend")) return rc;
+        if (int rc = ck(g_nccl.Recv(ghost + s->ghost_cap, nflt, ncclFloat, right, s->nccl_comm, q), "ncclRecv"))
             return rc;
     }
     if (int rc = ck(g_nccl.GroupEnd(), "ncclGroupEnd")) return rc;
@@ -717,25 +728,32 @@ int Ops::launch_substep(int phase) {
                          halo ? s->d_send_cnt.p : nullptr,
                          halo ? s->ghost_cap : 0u};
 
-    auto run_plan = [&](const LinkPlan &P, uint32_t base, const uint32_t *d_ps, const uint32_t *d_cs,
-                        const LocalLink *d_l, const GlobalLink *d_g, cudaStream_t q, bool fuse_count) -> int {
-        if (P.n_parts() && !P.local_links.empty()) {
+    // local partitions [p0, p1) of the plan; halo_mode: 0 none, 1 pack, 2 check only
+    auto run_local = [&](const LinkPlan &P, uint32_t base, const uint32_t *d_ps, const uint32_t *d_cs,
+                         const LocalLink *d_l, cudaStream_t q, bool fuse_count, uint32_t p0, uint32_t p1,
+                         int halo_mode) -> int {
+        if (p1 > p0 && !P.local_links.empty()) {
             uint32_t maxp = 0;
             for (uint32_t p = 0; p < P.n_parts(); p++) maxp = std::max(maxp, P.part_start[p + 1] - P.part_start[p]);
             size_t smem = (size_t)maxp * (K ? 12 : 8);
             const uint32_t T = s->k3_threads;
-            const uint32_t np = P.n_parts(), C = P.n_local_colours;
-            if (fuse_count && halo)  // strips: no inverse masses (checked in rebuild)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, true><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+            const uint32_t np = p1 - p0, C = P.n_local_colours;
+            if (fuse_count && halo_mode == 1)  // strips: no inverse masses (checked in rebuild)
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 1><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
+            else if (fuse_count && halo_mode == 2)
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 2><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
             else if (K && fuse_count)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, true, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, true, 0><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
             else if (K)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, false, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, false, 0><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
             else if (fuse_count)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 0><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
             else
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, false, false><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca));
+                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, false, 0><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
         }
+        return BENDY_OK;
+    };
+    auto run_global = [&](const LinkPlan &P, uint32_t base, const GlobalLink *d_g, cudaStream_t q) -> int {
         for (uint32_t c = 0; c < P.n_global_colours(); c++) {
             uint32_t l0 = P.gcolour_start[c], l1 = P.gcolour_start[c + 1];
             if (l0 == l1) continue;
@@ -793,9 +811,14 @@ int Ops::launch_substep(int phase) {
     // ---- particle chain: links (solver.rs:144-146) [+ histogram] -> scan -> scatter
     const uint32_t n_in_parts = s->plan_p.n_parts() ? s->plan_p.part_start.back() : 0u;
     const bool fuse_count = discs && s->plan_p.n_global_colours() == 0 && n_in_parts > 0;
-    if (int rc = run_plan(s->plan_p, 0, s->d_part_start.p, s->d_part_cs.p, s->d_local.p, s->d_global.p, st, fuse_count))
-        return rc;
-    if (discs) {  // histogram (+ halo packing) of the owned discs the link kernel did not cover
+    const LinkPlan &PP = s->plan_p;
+    const uint32_t n_parts = PP.n_parts();
+    // strips, graph mode: the partitions of the bodies near the halo bands run first, their discs are
+    // packed, and the NCCL exchange proceeds on a side stream WHILE the interior partitions are relaxed
+    const uint32_t nb = PP.n_priority_parts;
+    const bool overlap = halo && phase == PHASE_ALL && branch && fuse_count && s->nccl_comm && nb > 0 && nb < n_parts;
+    auto count_unlinked = [&]() -> int {  // histogram (+ halo packing) of the owned discs the link kernel did not cover
+        if (!discs) return BENDY_OK;
         const uint32_t c0 = fuse_count ? n_in_parts : 0u;
         if (c0 < s->nOwned) {
             if (halo)
@@ -803,20 +826,41 @@ int Ops::launch_substep(int phase) {
             else
                 LAUNCH(BENDY_K_GRID_BUILD, k2_count<false><<<cdiv(s->nOwned - c0, 256), 256, 0, st>>>(pos, c0, s->nOwned, ca));
         }
+        return BENDY_OK;
+    };
+    if (overlap) {
+        cudaStream_t qx = s->side[0];  // free in strip mode (no circles)
+        if (int rc = run_local(PP, 0, s->d_part_start.p, s->d_part_cs.p, s->d_local.p, st, true, 0, nb, 1)) return rc;
+        if (int rc = count_unlinked()) return rc;
+        CK(cudaEventRecord(s->ev_main, st));
+        CK(cudaStreamWaitEvent(qx, s->ev_main, 0));
+        if (int rc = halo_exchange_nccl(qx)) return rc;
+        LAUNCH(BENDY_K_HALO, k_halo_clear<<<cdiv(s->ghost_cap, 256), 256, 0, qx>>>(s->d_send[0].p, s->d_send[1].p,
+                                                                                   s->d_send_cnt.p, s->ghost_cap));
+        CK(cudaEventRecord(s->ev_xchg, qx));
+        if (int rc = run_local(PP, 0, s->d_part_start.p, s->d_part_cs.p, s->d_local.p, st, true, nb, n_parts, 2)) return rc;
+        CK(cudaStreamWaitEvent(st, s->ev_xchg, 0));
+        LAUNCH(BENDY_K_GRID_BUILD, k2_count<false><<<cdiv(s->nP - s->nOwned, 256), 256, 0, st>>>(pos, s->nOwned, s->nP, ca));
+        goto after_halo;
     }
+    if (int rc = run_local(PP, 0, s->d_part_start.p, s->d_part_cs.p, s->d_local.p, st, fuse_count, 0, n_parts, halo ? 1 : 0))
+        return rc;
+    if (int rc = run_global(PP, 0, s->d_global.p, st)) return rc;
+    if (int rc = count_unlinked()) return rc;
     }
     if (phase == PHASE_A) {
         CK(cudaEventRecord(s->ev_phase_a, st));
         return BENDY_OK;
     }
     if (halo && phase == PHASE_ALL)
-        if (int rc = halo_exchange_nccl()) return rc;
+        if (int rc = halo_exchange_nccl(st)) return rc;
 phase_b:
     if (halo) {  // my send buffers were consumed: reset them; then the received ghosts join the histogram
         LAUNCH(BENDY_K_HALO, k_halo_clear<<<cdiv(s->ghost_cap, 256), 256, 0, st>>>(s->d_send[0].p, s->d_send[1].p,
                                                                                    s->d_send_cnt.p, s->ghost_cap));
         LAUNCH(BENDY_K_GRID_BUILD, k2_count<false><<<cdiv(s->nP - s->nOwned, 256), 256, 0, st>>>(pos, s->nOwned, s->nP, ca));
     }
+after_halo:
     cudaStream_t qc = (branch && s->nC > 0) ? s->side[0] : st;
     cudaStream_t qg = (branch && nPoly > 0) ? s->side[1] : st;
     if (discs) {
@@ -1468,6 +1512,7 @@ static void fill_info(const LinkPlan &P, const LinkPlan *G, bendy_schedule_info 
     out->n_local_links = (uint32_t)P.local_links.size();
     out->n_global_links = (uint32_t)P.global_links.size();
     if (G) out->n_poly_partitions = G->n_parts();
+    out->n_priority_partitions = P.n_priority_parts;
 }
 
 int bendy_get_schedule_info(bendy_solver *s, bendy_schedule_info *out) {

@@ -121,7 +121,7 @@ typedef struct bendy_schedule_info {
     uint32_t n_global_links;
     uint32_t n_poly_partitions; /* partitions holding polygon-internal links */
     uint32_t kernels_per_substep;
-    uint32_t reserved;
+    uint32_t n_priority_partitions; /* strips: leading partitions relaxed before the halo exchange starts */
 } bendy_schedule_info;
 /* Builds the schedule if links changed, then reports it. */
 int bendy_get_schedule_info(bendy_solver *s, bendy_schedule_info *out);

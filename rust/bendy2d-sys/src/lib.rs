@@ -24,7 +24,7 @@ pub struct bendy_schedule_info {
     pub n_global_links: u32,
     pub n_poly_partitions: u32,
     pub kernels_per_substep: u32,
-    pub reserved: u32,
+    pub n_priority_partitions: u32,
 }
 
 extern "C" {

@@ -88,12 +88,13 @@ def _nccl_worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    sc = touching_field()
+    sc = touching_field(24, 2)  # wide enough that every strip has interior bodies (overlapped exchange path)
     sv = strips.StripSolver(sc, rank, world, rank, dist)
+    info = sv.schedule_info()
     sv.update(sc.dt, n=60)
     pos, prev = sv.read_particles()
     sv.check_halo()
-    q.put((rank, sv.part.global_index, pos, prev))
+    q.put((rank, sv.part.global_index, pos, prev, info))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -106,7 +107,7 @@ def test_nccl_strips_match_single_gpu():
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
 
-    sc = touching_field()
+    sc = touching_field(24, 2)
     ref = Solver(0)
     sc.load_into(ref)
     ref.update(sc.dt, n=60)
@@ -119,8 +120,9 @@ def test_nccl_strips_match_single_gpu():
         p.start()
     gp, gq = np.empty_like(rp), np.empty_like(rq)
     for _ in procs:
-        rank, idx, pos, prev = q.get(timeout=300)
+        rank, idx, pos, prev, info = q.get(timeout=300)
         gp[idx], gq[idx] = pos, prev
+        assert 0 < info["n_priority_partitions"] < info["n_partitions"], info
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
