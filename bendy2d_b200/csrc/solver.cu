@@ -166,6 +166,7 @@ struct bendy_solver {
     uint32_t scan_fused_capacity = 0;  // CTAs of k2_scan_fused that can be resident at once
     uint32_t k3_threads = 128;  // BENDY_K3_THREADS
     bool scatter_agg = false;   // BENDY_SCATTER_AGG
+    bool halo_overlap = false;  // BENDY_HALO_OVERLAP
     DevBuf<float2> d_sorted_pos;
     DevBuf<uint32_t> d_circ_tile_count, d_circ_tile_ids;
     uint32_t n_scan_tiles = 0, n_circ_tiles = 0;
@@ -422,7 +423,7 @@ int Ops::rebuild() {
     std::string perr;
     // strips: bodies close to a halo band are relaxed first so that the exchange can overlap the rest
     std::vector<uint8_t> prio;
-    if (s->halo_on && s->ghost_cap) {
+    if (s->halo_on && s->ghost_cap && s->halo_overlap) {
         const float gl = std::isfinite(s->halo_xl) ? (s->halo_xl - s->stray_xl) / 3.0f : 0.f;  // = band / 2
         const float gr = std::isfinite(s->halo_xr) ? (s->stray_xr - s->halo_xr) / 3.0f : 0.f;
         prio.resize(s->nOwned);
@@ -816,7 +817,10 @@ int Ops::launch_substep(int phase) {
     // strips, graph mode: the partitions of the bodies near the halo bands run first, their discs are
     // packed, and the NCCL exchange proceeds on a side stream WHILE the interior partitions are relaxed
     const uint32_t nb = PP.n_priority_parts;
-    const bool overlap = halo && phase == PHASE_ALL && branch && fuse_count && s->nccl_comm && nb > 0 && nb < n_parts;
+    // Measured on 8 x B200 (C5, 2M discs per rank): the split costs more than the exchange it hides
+    // (166 vs 153 us per substep), so it is opt-in (BENDY_HALO_OVERLAP=1).
+    const bool overlap = s->halo_overlap && halo && phase == PHASE_ALL && branch && fuse_count && s->nccl_comm &&
+                         nb > 0 && nb < n_parts;
     auto count_unlinked = [&]() -> int {  // histogram (+ halo packing) of the owned discs the link kernel did not cover
         if (!discs) return BENDY_OK;
         const uint32_t c0 = fuse_count ? n_in_parts : 0u;
@@ -1122,6 +1126,7 @@ bendy_solver *bendy_create(int device) {
         if (t >= 32 && t <= 1024 && t % 32 == 0) s->k3_threads = (uint32_t)t;
     }
     if (const char *v = getenv("BENDY_SCATTER_AGG")) s->scatter_agg = atoi(v) != 0;
+    if (const char *v = getenv("BENDY_HALO_OVERLAP")) s->halo_overlap = atoi(v) != 0;
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->side[0], cudaStreamNonBlocking)) != cudaSuccess ||
