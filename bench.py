@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scaling-ref", action="store_true", help="skip the C5-on-one-GPU reference point")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (not the headline)")
     ap.add_argument("--grid-cell", type=float, default=0.0, help="override the broadphase cell edge (0 = auto)")
     ap.add_argument("--pack-points", type=int, default=0, help="override the link-partition pack target")
@@ -371,9 +372,33 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         csc, what = cpu_baseline_sample(workload)
         t0 = time.perf_counter()
-        v, _ = time_oracle(csc, 3, 1)
-        cpu = {"value": v, "unit": "particle-substeps/s", "cores": 1, "kind": "port", "sample": what + ", 3 steps",
+        n_cpu_steps = 24 if workload != "c1" else 250  # ~10-20 s of single-core work
+        v, _ = time_oracle(csc, n_cpu_steps, 1)
+        cpu = {"value": v, "unit": "particle-substeps/s", "cores": 1, "kind": "port",
+               "sample": f"{what}, {n_cpu_steps} steps of {csc.sub_steps} substeps",
                "host_cores_available": os.cpu_count(), "seconds": time.perf_counter() - t0}
+
+    # ---- the 16M-particle scene on this one GPU: the N=1 point of the strong-scaling series that
+    # `bench.py --gpus 2|4|8` continues (those runs shard C5; this run's headline stays C3)
+    scaling_ref = None
+    if world == 1 and workload == "c3" and not args.no_scaling_ref:
+        del solver
+        sc5 = make_scene("c5")
+        s5 = Solver(local)
+        sc5.load_into(s5)
+        for _ in range(3):
+            s5.update(sc5.dt)
+        s5.synchronize()
+        n5, ms5 = 6, 0.0
+        for _ in range(n5):
+            flush_l2()
+            s5.timer_start()
+            s5.update(sc5.dt)
+            ms5 += s5.timer_stop()
+        scaling_ref = {"workload": sc5.name, "points": sc5.n_points, "n_gpus": 1, "steps": n5,
+                       "ms_per_step": ms5 / n5, "value": sc5.n_points * sc5.sub_steps * n5 / (ms5 * 1e-3),
+                       "unit": "particle-substeps/s"}
+        del s5
 
     line = {
         "metric": "particle-substeps/s", "value": value, "unit": "particle-substeps/s", "n_gpus": world,
@@ -387,7 +412,7 @@ def main():
         "value_warm_l2": value_warm, "wall_s_timed_region": wall,
         "ms_per_step_series": [round(x, 4) for x in step_ms],
         "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "schedule": info,
+        "schedule": info, "strong_scaling_reference_c5_n1": scaling_ref,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

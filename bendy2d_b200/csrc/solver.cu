@@ -171,6 +171,7 @@ struct bendy_solver {
     DevBuf<uint32_t> d_circ_tile_count, d_circ_tile_ids;
     uint32_t n_scan_tiles = 0, n_circ_tiles = 0;
     DevBuf<unsigned long long> d_circ_acc;
+    DevBuf<float2> d_circ_snap;
     uint32_t n_cells = 0;
     // polygons
     DevBuf<uint32_t> d_poly_start, d_poly_tiles;
@@ -536,6 +537,7 @@ int Ops::rebuild() {
         CK(cudaGetLastError());
     }
     if (s->nC) {
+        CK(s->d_circ_snap.ensure(s->nC));
         CK(s->d_circ_acc.ensure(2 * (size_t)s->nC));
         CK(cudaMemsetAsync(s->d_circ_acc.p, 0, 2 * (size_t)s->nC * sizeof(unsigned long long), s->stream));
     }
@@ -772,6 +774,7 @@ int Ops::launch_substep(int phase) {
     // of substep k+1, which never touches circle or polygon state before ITS join.
     const bool poly_work = nPoly > 0;
 
+    bool circ_joined = false;  // the circle chain's join event was already recorded (after the bins)
     if (phase == PHASE_B) goto phase_b;
     {
     // ---- polygon chain: centre (polygon.rs:219) -> own links (polygon.rs:220-222) -> AABB + obstacle bins
@@ -800,14 +803,23 @@ int Ops::launch_substep(int phase) {
     if (!s->cl.empty())
         LAUNCH(BENDY_K_LINKS_CIRCLE,
                k3_circle_links<<<1, 32, 0, qc>>>(pos + s->nP, s->d_crad.p, s->d_clinks.p, (uint32_t)s->cl.size()));
+    // the disc contacts (ext) are tested against the circle centres at the ENTRY of the collision phase
+    // (snapshot taken by the bin kernel), so the narrowphase only waits for the bins and the exact
+    // circle-circle pass below overlaps it; the circles' tail (apply + integrate) follows both.
+    if (discs && s->nC) {
+        LAUNCH(BENDY_K_CIRCLES, k2_circle_bin<<<cdiv(s->nC, 128), 128, 0, qc>>>(pos + s->nP, s->d_crad.p, s->nC, prm,
+                                                                                 s->d_circ_tile_count.p, s->d_circ_tile_ids.p,
+                                                                                 s->d_circ_snap.p));
+        if (branch && qc != st) {
+            CK(cudaEventRecord(s->ev_join[0], qc));
+            circ_joined = true;  // the main stream waits for this event before the narrowphase
+        }
+    }
     if (s->nC >= 2) {
         size_t smem = s->nC <= 4096 ? (size_t)s->nC * 12 : 0;
         LAUNCH(BENDY_K_CIRCLE_PASS,
                k_circles_exact<<<1, 1024, smem, qc>>>(pos + s->nP, s->d_crad.p, s->nC, smem ? 1 : 0, s->d_flags.p + 1));
     }
-    if (discs && s->nC)
-        LAUNCH(BENDY_K_CIRCLES, k2_circle_bin<<<cdiv(s->nC, 128), 128, 0, qc>>>(pos + s->nP, s->d_crad.p, s->nC, prm,
-                                                                                 s->d_circ_tile_count.p, s->d_circ_tile_ids.p));
 
     // ---- particle chain: links (solver.rs:144-146) [+ histogram] -> scan -> scatter
     const uint32_t n_in_parts = s->plan_p.n_parts() ? s->plan_p.part_start.back() : 0u;
@@ -896,7 +908,7 @@ after_halo:
     // ---- join: the collision phase needs all three worlds
     if (branch) {
         if (qc != st) {
-            CK(cudaEventRecord(s->ev_join[0], qc));
+            if (!circ_joined) CK(cudaEventRecord(s->ev_join[0], qc));
             CK(cudaStreamWaitEvent(st, s->ev_join[0], 0));
         }
         if (qg != st) {
@@ -913,7 +925,7 @@ after_halo:
         // narrowphase + polygon contact + bounds + integrate for the free particles, fused
         K2Args a{pos,     s->d_prev.p,   dk,    s->d_slot_of.p, s->d_sorted_id.p, s->d_sorted_pos.p, s->d_cell_start.p, s->n_cells,
                  s->nP,   s->nOwned,     s->nC, s->d_crad.p,             s->d_circ_tile_count.p,  s->d_circ_tile_ids.p,
-                 s->d_circ_acc.p};
+                 s->d_circ_acc.p, s->d_circ_snap.p};
         const uint32_t blocks = cdiv(s->nOwned, 128);
         if (K && contact)
             LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<true, true><<<blocks, 128, 0, st>>>(a, k4, prm));

@@ -362,14 +362,13 @@ static inline int cell_coord(float x, float o, float inv_h, int n) {
 // point and summed in int64, so the sum does not depend on the visiting order; the disc then moves
 // by pos + (float)sum.  A correction >= 2^-17 converts exactly, so for a contact graph that is a
 // matching this equals the reference's sequential pass bit-for-bit.  The grid only prunes pairs.
-static void ext_disc_contacts(bo_world &w) {
+static void ext_disc_contacts(bo_world &w, const std::vector<V2> &QC) {
     const size_t n = w.particles.size();
     const size_t nc = w.circles.size();
     if (n == 0) return;
     const float rp = w.particle_radius;
-    std::vector<V2> Q(n), QC(nc);
+    std::vector<V2> Q(n);
     for (size_t i = 0; i < n; i++) Q[i] = w.particles[i].pos;
-    for (size_t c = 0; c < nc; c++) QC[c] = w.circles[c].point.pos;
 
     const int nx = w.grid_nx, ny = w.grid_ny;
     std::vector<uint32_t> cell(n);
@@ -456,7 +455,9 @@ static void ext_disc_contacts(bo_world &w) {
     for (size_t i = 0; i < n; i++) w.particles[i].pos = out[i];
     for (size_t c = 0; c < nc; c++) {
         if (accx[c] == 0 && accy[c] == 0) continue;
-        w.circles[c].point.pos = v2(QC[c].x + from_fix(accx[c]), QC[c].y + from_fix(accy[c]));
+        // the Circle receives its share AFTER the reference's circle-circle pass has run
+        V2 cur = w.circles[c].point.pos;
+        w.circles[c].point.pos = v2(cur.x + from_fix(accx[c]), cur.y + from_fix(accy[c]));
     }
 }
 
@@ -545,6 +546,14 @@ static void ext_polygon_contacts(bo_world &w) {
 
 // solver.rs:167-188
 static void solve_dynamic_collisions(bo_world &w) {
+    // ext: the disc contacts below are tested against the circle centres at phase ENTRY (a Jacobi
+    // snapshot, like the particle positions), so that on the device the circle-circle pass can
+    // overlap the narrowphase
+    std::vector<V2> circle_entry;
+    if (w.particle_radius > 0.0f) {
+        circle_entry.resize(w.circles.size());
+        for (size_t c = 0; c < w.circles.size(); c++) circle_entry[c] = w.circles[c].point.pos;
+    }
     size_t length = w.circles.size();
     for (size_t i = 0; i < length; i++)
         for (size_t j = i + 1; j < length; j++) circle_solve_circle(w.circles[i], w.circles[j]);
@@ -552,7 +561,7 @@ static void solve_dynamic_collisions(bo_world &w) {
     for (size_t i = 0; i < length; i++)
         for (size_t j = i + 1; j < length; j++) solve_polygon(w.polygons[i], w.polygons[j]);
     // ext phases (off by default => reference semantics)
-    if (w.particle_radius > 0.0f) ext_disc_contacts(w);
+    if (w.particle_radius > 0.0f) ext_disc_contacts(w, circle_entry);
     if (w.polygon_contact) ext_polygon_contacts(w);
 }
 

@@ -59,7 +59,7 @@ def test_kat_integration_bits():
     ys = []
     for _ in range(3):
         g.update(dt)
-        ys.append(int(bits(g.read_particles()[0][0, 1])))
+        ys.append(int(bits(g.read_particles()[0][0, 1]).item()))
     assert ys == [0x42480070, 0x42480150, 0x424802A0]
 
 

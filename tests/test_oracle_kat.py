@@ -36,7 +36,7 @@ def test_k_int_2_bits():
     ys = []
     for _ in range(3):
         s.update(float(dt))
-        ys.append(int(bits(s.particles()[0][0, 1])))
+        ys.append(int(bits(s.particles()[0][0, 1]).item()))
     assert ys == [0x42480070, 0x42480150, 0x424802A0]
     # independent numpy evaluation of (pos+vel)+((acc*dt)*dt)
     pos, prev, g = f32(50.0), f32(50.0), f32(98.2)
