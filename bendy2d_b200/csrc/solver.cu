@@ -1171,6 +1171,9 @@ bendy_solver *bendy_clone(bendy_solver *s) {
     c->gl_ab = s->gl_ab, c->gl_len = s->gl_len, c->any_acc = s->any_acc;
     c->sub_steps = s->sub_steps, c->particle_radius = s->particle_radius, c->grid_cell = s->grid_cell;
     c->polygon_contact = s->polygon_contact, c->plan_params = s->plan_params;
+    // strip configuration travels too; the transport (NCCL communicator / local peers) does not
+    c->halo_on = s->halo_on, c->ghost_cap = s->ghost_cap, c->halo_xl = s->halo_xl, c->halo_xr = s->halo_xr;
+    c->stray_xl = s->stray_xl, c->stray_xr = s->stray_xr, c->win_x0 = s->win_x0, c->win_x1 = s->win_x1;
     return c;
 }
 
