@@ -783,16 +783,14 @@ int Ops::launch_substep(int phase) {
     PolyArgs pa{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_static.p, nPoly, s->d_poly_center.p,
                 s->d_poly_box.p,     s->d_poly_tiles.p, s->d_flags.p, s->d_poly_first_row.p};
     if (poly_work) {
-        LAUNCH(BENDY_K_POLY_PREP, k4_poly_center<<<cdiv(nPoly, 128), 128, 0, qg>>>(pa));
-        if (!s->gl_len.empty())
-            LAUNCH(BENDY_K_LINKS_LOCAL, k3_polygon_links<<<cdiv(nPoly, 128), 128, 0, qg>>>(
-                                            pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_link_start.p,
-                                            s->d_poly_link_ab.p, s->d_poly_link_len.p, nPoly));
-        if (contact || nPoly >= 2) {
+        // centre -> own links -> AABB -> bins, one thread per polygon, one launch
+        const bool bins = contact || nPoly >= 2;
+        if (bins)
             LAUNCH(BENDY_K_POLY_PREP, cudaMemsetAsync(s->d_poly_tiles.p, 0,
                                                       (size_t)s->n_poly_tiles * (BENDY_POLY_CAP + 1) * sizeof(uint32_t), qg));
-            LAUNCH(BENDY_K_POLY_PREP, k4_poly_box_bin<<<cdiv(nPoly, 128), 128, 0, qg>>>(pa, prm));
-        }
+        PolyLinkArgs la{s->d_poly_link_start.p, s->d_poly_link_ab.p, s->d_poly_link_len.p};
+        LAUNCH(BENDY_K_POLY_PREP,
+               k_poly_prepare<<<cdiv(nPoly, 128), 128, 0, qg>>>(pos + s->nP + s->nC, pa, la, prm, bins ? 1 : 0));
         if (nPoly >= 2) {  // solve_dynamic_collisions, polygon half (solver.rs:178-187)
             LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_pair_prescan<<<cdiv(nPoly, 128), 128, 0, qg>>>(pa, prm));
             LAUNCH(BENDY_K_POLY_CONTACT,
