@@ -24,7 +24,7 @@ ERR_NAMES = {-1: "BENDY_ERR_ARG", -2: "BENDY_ERR_LINK", -3: "BENDY_ERR_CUDA", -4
              -5: "BENDY_ERR_NO_DEVICE"}
 
 K_CLASSES = ["integrate", "links_local", "links_global", "links_circle", "grid_build", "narrowphase", "circles",
-             "poly_prep", "poly_contact", "halo", "circle_pass"]
+             "poly_prep", "poly_contact", "fused", "halo", "circle_pass"]
 
 
 class ScheduleInfo(C.Structure):

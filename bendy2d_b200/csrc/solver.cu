@@ -167,6 +167,7 @@ struct bendy_solver {
     uint32_t k3_threads = 128;  // BENDY_K3_THREADS
     bool scatter_agg = false;   // BENDY_SCATTER_AGG
     bool halo_overlap = false;  // BENDY_HALO_OVERLAP
+    bool small_scene = true;    // BENDY_SMALL_SCENE=0 forces the multi-kernel path for tiny scenes
     DevBuf<float2> d_sorted_pos;
     DevBuf<uint32_t> d_circ_tile_count, d_circ_tile_ids;
     uint32_t n_scan_tiles = 0, n_circ_tiles = 0;
@@ -1048,6 +1049,19 @@ int Ops::enqueue_substeps(uint32_t updates) {
         done = 1;
     }
     if (done == updates) return BENDY_OK;
+    // small scenes: one launch per update() with all its substeps (see k_small_scene)
+    const bool small = s->small_scene && !s->profiling && !s->halo_on && !s->has_k && s->polys.empty() && s->nC <= 1 &&
+                       s->cl.empty() && !(s->particle_radius > 0.f) && s->N > 0 && s->N <= 3072 &&
+                       s->plan_p.n_parts() <= 1 && s->plan_p.global_links.empty() &&
+                       (s->plan_p.n_parts() == 0 || s->plan_p.part_start[0] == 0);
+    if (small) {
+        K1Args k1{s->d_pos.p, s->d_prev.p, nullptr, nullptr, s->d_crad.p, s->d_gstatic.p, s->nP, s->nC, s->N};
+        const uint32_t C = s->plan_p.n_parts() ? s->plan_p.n_local_colours : 0u;
+        for (uint32_t u = done; u < updates; u++)
+            LAUNCH(BENDY_K_FUSED, k_small_scene<<<1, 256, (size_t)s->N * 16, s->stream>>>(
+                                      k1, s->d_part_cs.p, s->d_local.p, C, s->d_prm.p, S));
+        return BENDY_OK;
+    }
     if (s->profiling) {
         for (uint32_t u = done; u < updates; u++)
             for (uint32_t k = 0; k < S; k++)
@@ -1137,6 +1151,7 @@ bendy_solver *bendy_create(int device) {
     }
     if (const char *v = getenv("BENDY_SCATTER_AGG")) s->scatter_agg = atoi(v) != 0;
     if (const char *v = getenv("BENDY_HALO_OVERLAP")) s->halo_overlap = atoi(v) != 0;
+    if (const char *v = getenv("BENDY_SMALL_SCENE")) s->small_scene = atoi(v) != 0;
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->side[0], cudaStreamNonBlocking)) != cudaSuccess ||

@@ -145,6 +145,7 @@ enum {
     BENDY_K_CIRCLES,       /* circle-circle lexicographic pass + circle binning/apply */
     BENDY_K_POLY_PREP,     /* polygon centre / AABB / binning */
     BENDY_K_POLY_CONTACT,  /* K4 particle-polygon closest edge (+ polygon-polygon) */
+    BENDY_K_FUSED,         /* small scenes: all substeps of an update in one single-CTA launch */
     BENDY_K_HALO,          /* strips: halo exchange (NCCL send/recv or peer copy) + send-buffer reset */
     BENDY_K_CIRCLE_PASS,   /* exact circle-circle pass (solver.rs:168-177) */
     BENDY_K_CLASSES

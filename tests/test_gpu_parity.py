@@ -189,6 +189,29 @@ def test_c1_long_run_drift_and_energy():
     assert np.isfinite(gp).all() and (gp >= 0).all() and (gp <= 100).all()
 
 
+def test_small_scene_single_launch_equals_multi_kernel_path():
+    """C1 takes the one-launch-per-update path (k_small_scene); forcing the multi-kernel graph path
+    must give the same bits, and the single-launch path must really have been used."""
+    import os
+
+    sc = scenes.c1_softbody_blob()
+    a = Solver()
+    os.environ["BENDY_SMALL_SCENE"] = "0"
+    try:
+        b = Solver()
+    finally:
+        del os.environ["BENDY_SMALL_SCENE"]
+    sc.load_into(a)
+    sc.load_into(b)
+    a.update(sc.dt, n=40)
+    b.update(sc.dt, n=40)
+    pa, qa = a.read_particles()
+    pb, qb = b.read_particles()
+    assert np.array_equal(bits(pa), bits(pb)) and np.array_equal(bits(qa), bits(qb))
+    assert np.array_equal(bits(a.read_circles()[0]), bits(b.read_circles()[0]))
+    assert 40 <= a.launch_count() <= 44 and b.launch_count() > 40 * 8  # 40 fused launches + read-back gathers
+
+
 def test_sub_steps_equals_repeated_updates():
     sc = scenes.c1_softbody_blob()
     a, b = Solver(), Solver()
