@@ -338,8 +338,16 @@ def main():
     grid = solver.grid() if sc.particle_radius > 0 else None
     shard = solver.local_scene() if world > 1 else sc
     alg = shard.algorithmic_bytes(grid)
-    class_bytes = {"integrate": alg["K1_integrate"], "links_local": alg["K3_links"], "links_global": 0,
-                   "grid_build": alg["K2_grid"], "narrowphase": alg["K2_narrow"], "poly_contact": alg["K4_polygon"],
+    # kernel class -> algorithmic bytes per substep (SURVEY §8.4 per-unit figures x the units it processes).
+    # With the disc grid on, the narrowphase launch ALSO does the particle-polygon contact (K4) and the
+    # bounds+integrate (K1) of the free particles, so those bytes belong to it; the separate integrate
+    # launch then only covers circle centres and polygon points.
+    discs_on = shard.particle_radius > 0 and shard.n_particles > 0
+    k1_particles = shard.n_particles * 32
+    class_bytes = {"integrate": alg["K1_integrate"] - (k1_particles if discs_on else 0),
+                   "links_local": alg["K3_links"], "links_global": 0, "grid_build": alg["K2_grid"],
+                   "narrowphase": alg["K2_narrow"] + (k1_particles + alg["K4_polygon"] if discs_on else 0),
+                   "poly_contact": 0 if discs_on else alg["K4_polygon"],
                    "fused": alg["K1_integrate"] + alg["K3_links"]}
     kernels = {}
     total_k_ms = sum(v["ms"] for v in kt.values())
