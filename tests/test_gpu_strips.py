@@ -81,6 +81,14 @@ def test_strip_group_sub_steps():
 
 
 def _nccl_worker(rank, world, port, q):
+    try:
+        _nccl_worker_body(rank, world, port, q)
+    except Exception as e:  # report instead of leaving the parent waiting for the queue
+        q.put((rank, None, None, None, f"{type(e).__name__}: {e}"))
+        raise
+
+
+def _nccl_worker_body(rank, world, port, q):
     import torch
     import torch.distributed as dist
 
@@ -121,6 +129,7 @@ def test_nccl_strips_match_single_gpu():
     gp, gq = np.empty_like(rp), np.empty_like(rq)
     for _ in procs:
         rank, idx, pos, prev, info = q.get(timeout=300)
+        assert idx is not None, f"rank {rank} failed: {info}"
         gp[idx], gq[idx] = pos, prev
         assert info["n_partitions"] > 0, info
     for p in procs:
