@@ -1051,7 +1051,7 @@ int Ops::enqueue_substeps(uint32_t updates) {
     if (done == updates) return BENDY_OK;
     // small scenes: one launch per update() with all its substeps (see k_small_scene)
     const bool small = s->small_scene && !s->profiling && !s->halo_on && !s->has_k && s->polys.empty() && s->nC <= 1 &&
-                       s->cl.empty() && !(s->particle_radius > 0.f) && s->N > 0 && s->N <= 3072 &&
+                       s->cl.empty() && !(s->particle_radius > 0.f) && s->N > 0 && s->N <= 2900 &&
                        s->plan_p.n_parts() <= 1 && s->plan_p.global_links.empty() &&
                        (s->plan_p.n_parts() == 0 || s->plan_p.part_start[0] == 0);
     if (small) {
