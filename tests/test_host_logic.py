@@ -124,3 +124,25 @@ def test_scene_sizes_match_survey():
     assert sc.n_particles == 5000 and len(sc.circles_r) == 4 and len(sc.polygons) == 3
     b = sc.algorithmic_bytes()
     assert b["K3_links"] == (sc.n_links + 18) * 44 and b["K1_integrate"] == sc.n_points * 32
+
+
+def test_header_is_plain_c_and_every_entry_point_links(tmp_path):
+    """gcc -std=c99 -Wall -Werror on a C program with one typed call site per entry point."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(_lib.build())
+    exe = str(tmp_path / "c_abi_check")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_check.c"), "-o", exe, "-L" + libdir, "-lbendy2d_b200",
+                           "-Wl,-rpath," + libdir])
+    src = open(os.path.join(ROOT, "tests", "c_abi_check.c")).read()
+    hdr = open(os.path.join(ROOT, "include", "bendy2d_b200.h")).read()
+    declared = set(re.findall(r"\b(bendy_[a-z0-9_]+)\s*\(", hdr)) - {"bendy_solver", "bendy_schedule_info"}
+    missing = [n for n in sorted(declared) if n + "(" not in src]
+    assert not missing, f"c_abi_check.c does not call {missing}"
+    # runs anywhere: without a GPU it stops after bendy_create fails loudly
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
