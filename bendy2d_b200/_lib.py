@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbendy2d_b200.so")
+# BENDY2D_B200_LIB points at an alternative build of the same sources (tuning experiments)
+LIB_PATH = os.environ.get("BENDY2D_B200_LIB") or os.path.join(_HERE, "lib", "libbendy2d_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 f32p = C.POINTER(C.c_float)
