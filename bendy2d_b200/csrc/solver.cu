@@ -234,6 +234,20 @@ namespace {
         if (_e != cudaSuccess) return this->fail_cuda(_e, #call, __LINE__);                           \
     } while (0)
 
+// per-call constants of one substep launch sequence
+struct SubstepCtx {
+    cudaStream_t st, qc, qg;  // main / circle-chain / polygon-chain streams (all == st when not capturing)
+    const StepParams *prm;
+    float2 *pos;
+    const float *dk;
+    bool K, discs, contact, halo, branch, acc, fuse_count;
+    bool circ_joined;  // the circle chain's join event was already recorded (after the bins)
+    uint32_t nPoly, n_in_parts;
+    K3CountArgs ca;
+    K1Args k1;
+    K4Args k4;
+};
+
 struct Ops {  // helper with access to the solver; keeps bendy_solver a plain struct
     bendy_solver *s;
     int fail(int code, const std::string &msg) {
@@ -264,6 +278,17 @@ struct Ops {  // helper with access to the solver; keeps bendy_solver a plain st
     int enqueue_substeps(uint32_t count);
     int launch_substep(int phase = PHASE_ALL);
     int halo_exchange_nccl(cudaStream_t q);
+    SubstepCtx make_ctx();
+    int launch_links_local(const SubstepCtx &c, cudaStream_t q, uint32_t p0, uint32_t p1, int halo_mode);
+    int launch_links_global(const SubstepCtx &c, cudaStream_t q);
+    int launch_polygon_chain(const SubstepCtx &c);
+    int launch_circle_chain(SubstepCtx &c);
+    int launch_count_unlinked(const SubstepCtx &c);
+    int launch_halo_receive(const SubstepCtx &c, cudaStream_t q_clear);
+    int launch_particle_links(const SubstepCtx &c, int phase, bool *ghosts_done);
+    int launch_grid_build(const SubstepCtx &c);
+    int launch_collide_integrate_discs(const SubstepCtx &c);
+    int launch_collide_integrate_plain(const SubstepCtx &c);
     int build_graph(uint32_t substeps);
     void drop_graph();
     int flush_events();
@@ -711,290 +736,329 @@ int Ops::halo_exchange_nccl(cudaStream_t q) {
     return BENDY_OK;
 }
 
-// phase: PHASE_ALL = the whole substep (NCCL exchange in-stream); PHASE_A = up to the halo packing;
-// PHASE_B = from the ghost histogram on (bendy_update_group moves the halo between A and B).
-int Ops::launch_substep(int phase) {
-    cudaStream_t st = s->stream;
-    const StepParams *prm = s->d_prm.p;
-    const bool K = s->has_k;
-    float2 *pos = s->d_pos.p;
-    const uint32_t nPoly = (uint32_t)s->polys.size();
-    const bool contact = s->polygon_contact && nPoly && s->nP;
-    const bool discs = s->particle_radius > 0.f && s->nP;
-    const bool branch = s->capturing;
-    const float *dk = K ? s->d_k.p : nullptr;
-    const bool halo = s->halo_on && discs && s->ghost_cap > 0;
-    const K3CountArgs ca{prm,
-                         s->n_cells,
-                         s->d_cell_count.p,
-                         halo ? s->d_send[0].p : nullptr,
-                         halo ? s->d_send[1].p : nullptr,
-                         halo ? s->d_send_cnt.p : nullptr,
-                         halo ? s->ghost_cap : 0u};
+// ------------------------------------------------------------------------------------------------
+// One substep, reference order (solver.rs:109-115):
+//   gravity (fused into integrate) -> links -> dynamic collisions -> bounds -> integrate.
+// Free particles, circles and polygon points are disjoint worlds until the collision phase
+// (solver.rs:143-153).  While a graph is being captured the side streams were forked from the main
+// stream by build_graph(): the circle chain runs on side[0], the polygon chain on side[1]; their
+// tails (integrate) of substep k are queued behind the narrowphase of substep k and overlap the
+// particle chain of substep k+1, which never touches circle or polygon state before ITS join.
+// Eager (profiling) launches are simply serial on the main stream.
+SubstepCtx Ops::make_ctx() {
+    SubstepCtx c{};
+    c.st = s->stream;
+    c.branch = s->capturing;
+    c.nPoly = (uint32_t)s->polys.size();
+    c.qc = (c.branch && s->nC > 0) ? s->side[0] : c.st;
+    c.qg = (c.branch && c.nPoly > 0) ? s->side[1] : c.st;
+    c.prm = s->d_prm.p;
+    c.pos = s->d_pos.p;
+    c.K = s->has_k;
+    c.dk = c.K ? s->d_k.p : nullptr;
+    c.discs = s->particle_radius > 0.f && s->nP;
+    c.contact = s->polygon_contact && c.nPoly && s->nP;
+    c.halo = s->halo_on && c.discs && s->ghost_cap > 0;
+    c.acc = s->accel_pending;
+    c.ca = K3CountArgs{c.prm,
+                       s->n_cells,
+                       s->d_cell_count.p,
+                       c.halo ? s->d_send[0].p : nullptr,
+                       c.halo ? s->d_send[1].p : nullptr,
+                       c.halo ? s->d_send_cnt.p : nullptr,
+                       c.halo ? s->ghost_cap : 0u};
+    const LinkPlan &P = s->plan_p;
+    c.n_in_parts = P.n_parts() ? P.part_start.back() : 0u;
+    c.fuse_count = c.discs && P.n_global_colours() == 0 && c.n_in_parts > 0;
+    c.k1 = K1Args{c.pos, s->d_prev.p, c.acc ? s->d_accel.p : nullptr, c.dk, s->d_crad.p, s->d_gstatic.p, s->nP, s->nC, s->N};
+    c.k4 = K4Args{c.pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_center.p, s->d_poly_box.p, s->d_poly_tiles.p,
+                  s->d_poly_static.p};
+    return c;
+}
 
-    // local partitions [p0, p1) of the plan; halo_mode: 0 none, 1 pack, 2 check only
-    auto run_local = [&](const LinkPlan &P, uint32_t base, const uint32_t *d_ps, const uint32_t *d_cs,
-                         const LocalLink *d_l, cudaStream_t q, bool fuse_count, uint32_t p0, uint32_t p1,
-                         int halo_mode) -> int {
-        if (p1 > p0 && !P.local_links.empty()) {
-            uint32_t maxp = 0;
-            for (uint32_t p = 0; p < P.n_parts(); p++) maxp = std::max(maxp, P.part_start[p + 1] - P.part_start[p]);
-            size_t smem = (size_t)maxp * (K ? 12 : 8);
-            const uint32_t T = s->k3_threads;
-            const uint32_t np = p1 - p0, C = P.n_local_colours;
-            if (fuse_count && halo_mode == 1)  // strips: no inverse masses (checked in rebuild)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 1><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
-            else if (fuse_count && halo_mode == 2)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 2><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
-            else if (K && fuse_count)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, true, 0><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
-            else if (K)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, false, 0><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
-            else if (fuse_count)
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 0><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
-            else
-                LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, false, 0><<<np, T, smem, q>>>(pos, dk, base, d_ps, d_cs, d_l, C, ca, p0));
-        }
-        return BENDY_OK;
-    };
-    auto run_global = [&](const LinkPlan &P, uint32_t base, const GlobalLink *d_g, cudaStream_t q) -> int {
-        for (uint32_t c = 0; c < P.n_global_colours(); c++) {
-            uint32_t l0 = P.gcolour_start[c], l1 = P.gcolour_start[c + 1];
-            if (l0 == l1) continue;
-            if (K)
-                LAUNCH(BENDY_K_LINKS_GLOBAL, k3_links_global<true><<<cdiv(l1 - l0, 256), 256, 0, q>>>(pos, dk, base, d_g, l0, l1));
-            else
-                LAUNCH(BENDY_K_LINKS_GLOBAL, k3_links_global<false><<<cdiv(l1 - l0, 256), 256, 0, q>>>(pos, dk, base, d_g, l0, l1));
-        }
-        return BENDY_OK;
-    };
+// shared-memory partitions [p0, p1) of the particle link plan; halo_mode: 0 none, 1 pack, 2 check only
+int Ops::launch_links_local(const SubstepCtx &c, cudaStream_t q, uint32_t p0, uint32_t p1, int halo_mode) {
+    const LinkPlan &P = s->plan_p;
+    if (p1 <= p0 || P.local_links.empty()) return BENDY_OK;
+    uint32_t maxp = 0;
+    for (uint32_t p = 0; p < P.n_parts(); p++) maxp = std::max(maxp, P.part_start[p + 1] - P.part_start[p]);
+    const size_t smem = (size_t)maxp * (c.K ? 12 : 8);
+    const uint32_t T = s->k3_threads, np = p1 - p0, C = P.n_local_colours;
+    const uint32_t *ps = s->d_part_start.p, *cs = s->d_part_cs.p;
+    const LocalLink *ll = s->d_local.p;
+    float2 *pos = c.pos;
+    const float *dk = c.dk;
+    const K3CountArgs &ca = c.ca;
+    if (c.fuse_count && halo_mode == 1)  // strips: no inverse masses (checked in rebuild)
+        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 1><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+    else if (c.fuse_count && halo_mode == 2)
+        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 2><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+    else if (c.K && c.fuse_count)
+        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, true, 0><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+    else if (c.K)
+        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, false, 0><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+    else if (c.fuse_count)
+        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 0><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+    else
+        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, false, 0><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+    return BENDY_OK;
+}
 
-    // While capturing, the side streams were forked from the main stream by build_graph(); the
-    // circle chain runs on side[0], the polygon chain on side[1].  Their tails (integrate) of
-    // substep k are queued behind the narrowphase of substep k and overlap the particle chain
-    // of substep k+1, which never touches circle or polygon state before ITS join.
-    const bool poly_work = nPoly > 0;
-
-    bool circ_joined = false;  // the circle chain's join event was already recorded (after the bins)
-    if (phase == PHASE_B) goto phase_b;
-    {
-    // ---- polygon chain: centre (polygon.rs:219) -> own links (polygon.rs:220-222) -> AABB + obstacle bins
-    cudaStream_t qc = (branch && s->nC > 0) ? s->side[0] : st;
-    cudaStream_t qg = (branch && nPoly > 0) ? s->side[1] : st;
-    PolyArgs pa{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_static.p, nPoly, s->d_poly_center.p,
-                s->d_poly_box.p,     s->d_poly_tiles.p, s->d_flags.p, s->d_poly_first_row.p};
-    if (poly_work) {
-        // centre -> own links -> AABB -> bins, one thread per polygon, one launch
-        const bool bins = contact || nPoly >= 2;
-        if (bins)
-            LAUNCH(BENDY_K_POLY_PREP, cudaMemsetAsync(s->d_poly_tiles.p, 0,
-                                                      (size_t)s->n_poly_tiles * (BENDY_POLY_CAP + 1) * sizeof(uint32_t), qg));
-        PolyLinkArgs la{s->d_poly_link_start.p, s->d_poly_link_ab.p, s->d_poly_link_len.p};
-        LAUNCH(BENDY_K_POLY_PREP,
-               k_poly_prepare<<<cdiv(nPoly, 128), 128, 0, qg>>>(pos + s->nP + s->nC, pa, la, prm, bins ? 1 : 0));
-        if (nPoly >= 2) {  // solve_dynamic_collisions, polygon half (solver.rs:178-187)
-            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_pair_prescan<<<cdiv(nPoly, 128), 128, 0, qg>>>(pa, prm));
-            LAUNCH(BENDY_K_POLY_CONTACT,
-                   k_polygons_exact<<<1, 1024, 0, qg>>>(pos + s->nP + s->nC, pa, prm, s->n_poly_tiles));
-        }
+// links across partitions: one launch per global colour, after all local colours
+int Ops::launch_links_global(const SubstepCtx &c, cudaStream_t q) {
+    const LinkPlan &P = s->plan_p;
+    for (uint32_t col = 0; col < P.n_global_colours(); col++) {
+        const uint32_t l0 = P.gcolour_start[col], l1 = P.gcolour_start[col + 1];
+        if (l0 == l1) continue;
+        if (c.K)
+            LAUNCH(BENDY_K_LINKS_GLOBAL,
+                   k3_links_global<true><<<cdiv(l1 - l0, 256), 256, 0, q>>>(c.pos, c.dk, 0, s->d_global.p, l0, l1));
+        else
+            LAUNCH(BENDY_K_LINKS_GLOBAL,
+                   k3_links_global<false><<<cdiv(l1 - l0, 256), 256, 0, q>>>(c.pos, c.dk, 0, s->d_global.p, l0, l1));
     }
-    // ---- circle chain: circle links (solver.rs:147-149) -> circle-circle pass (solver.rs:168-177) -> bins
+    return BENDY_OK;
+}
+
+// polygon chain: centre (polygon.rs:219) -> own links (polygon.rs:220-222) -> AABB + bins, then the
+// polygon half of solve_dynamic_collisions (solver.rs:178-187)
+int Ops::launch_polygon_chain(const SubstepCtx &c) {
+    if (!c.nPoly) return BENDY_OK;
+    float2 *pts = c.pos + s->nP + s->nC;
+    PolyArgs pa{pts,          s->d_poly_start.p, s->d_poly_static.p, c.nPoly, s->d_poly_center.p, s->d_poly_box.p,
+                s->d_poly_tiles.p, s->d_flags.p,      s->d_poly_first_row.p};
+    const bool bins = c.contact || c.nPoly >= 2;
+    if (bins)
+        LAUNCH(BENDY_K_POLY_PREP, cudaMemsetAsync(s->d_poly_tiles.p, 0,
+                                                  (size_t)s->n_poly_tiles * (BENDY_POLY_CAP + 1) * sizeof(uint32_t), c.qg));
+    PolyLinkArgs la{s->d_poly_link_start.p, s->d_poly_link_ab.p, s->d_poly_link_len.p};
+    LAUNCH(BENDY_K_POLY_PREP, k_poly_prepare<<<cdiv(c.nPoly, 128), 128, 0, c.qg>>>(pts, pa, la, c.prm, bins ? 1 : 0));
+    if (c.nPoly >= 2) {
+        LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_pair_prescan<<<cdiv(c.nPoly, 128), 128, 0, c.qg>>>(pa, c.prm));
+        LAUNCH(BENDY_K_POLY_CONTACT, k_polygons_exact<<<1, 1024, 0, c.qg>>>(pts, pa, c.prm, s->n_poly_tiles));
+    }
+    return BENDY_OK;
+}
+
+// circle chain: circle links (solver.rs:147-149) -> bins + entry snapshot -> circle-circle pass
+// (solver.rs:168-177).  The disc contacts (ext) are tested against the circle centres at the ENTRY of
+// the collision phase (the snapshot), so the narrowphase only waits for the bins (join event
+// recorded here) and the exact pass overlaps it; the circles' tail follows both.
+int Ops::launch_circle_chain(SubstepCtx &c) {
+    float2 *cpos = c.pos + s->nP;
     if (!s->cl.empty())
-        LAUNCH(BENDY_K_LINKS_CIRCLE,
-               k3_circle_links<<<1, 32, 0, qc>>>(pos + s->nP, s->d_crad.p, s->d_clinks.p, (uint32_t)s->cl.size()));
-    // the disc contacts (ext) are tested against the circle centres at the ENTRY of the collision phase
-    // (snapshot taken by the bin kernel), so the narrowphase only waits for the bins and the exact
-    // circle-circle pass below overlaps it; the circles' tail (apply + integrate) follows both.
-    if (discs && s->nC) {
-        LAUNCH(BENDY_K_CIRCLES, k2_circle_bin<<<cdiv(s->nC, 128), 128, 0, qc>>>(pos + s->nP, s->d_crad.p, s->nC, prm,
-                                                                                 s->d_circ_tile_count.p, s->d_circ_tile_ids.p,
-                                                                                 s->d_circ_snap.p));
-        if (branch && qc != st) {
-            CK(cudaEventRecord(s->ev_join[0], qc));
-            circ_joined = true;  // the main stream waits for this event before the narrowphase
+        LAUNCH(BENDY_K_LINKS_CIRCLE, k3_circle_links<<<1, 32, 0, c.qc>>>(cpos, s->d_crad.p, s->d_clinks.p, (uint32_t)s->cl.size()));
+    if (c.discs && s->nC) {
+        LAUNCH(BENDY_K_CIRCLES, k2_circle_bin<<<cdiv(s->nC, 128), 128, 0, c.qc>>>(cpos, s->d_crad.p, s->nC, c.prm,
+                                                                                   s->d_circ_tile_count.p,
+                                                                                   s->d_circ_tile_ids.p, s->d_circ_snap.p));
+        if (c.branch && c.qc != c.st) {
+            CK(cudaEventRecord(s->ev_join[0], c.qc));
+            c.circ_joined = true;
         }
     }
     if (s->nC >= 2) {
-        size_t smem = s->nC <= 4096 ? (size_t)s->nC * 12 : 0;
+        const size_t smem = s->nC <= 4096 ? (size_t)s->nC * 12 : 0;
         LAUNCH(BENDY_K_CIRCLE_PASS,
-               k_circles_exact<<<1, 1024, smem, qc>>>(pos + s->nP, s->d_crad.p, s->nC, smem ? 1 : 0, s->d_flags.p + 1));
-    }
-
-    // ---- particle chain: links (solver.rs:144-146) [+ histogram] -> scan -> scatter
-    const uint32_t n_in_parts = s->plan_p.n_parts() ? s->plan_p.part_start.back() : 0u;
-    const bool fuse_count = discs && s->plan_p.n_global_colours() == 0 && n_in_parts > 0;
-    const LinkPlan &PP = s->plan_p;
-    const uint32_t n_parts = PP.n_parts();
-    // strips, graph mode: the partitions of the bodies near the halo bands run first, their discs are
-    // packed, and the NCCL exchange proceeds on a side stream WHILE the interior partitions are relaxed
-    const uint32_t nb = PP.n_priority_parts;
-    // Measured on 8 x B200 (C5, 2M discs per rank): the split costs more than the exchange it hides
-    // (166 vs 153 us per substep), so it is opt-in (BENDY_HALO_OVERLAP=1).
-    const bool overlap = s->halo_overlap && halo && phase == PHASE_ALL && branch && fuse_count && s->nccl_comm &&
-                         nb > 0 && nb < n_parts;
-    auto count_unlinked = [&]() -> int {  // histogram (+ halo packing) of the owned discs the link kernel did not cover
-        if (!discs) return BENDY_OK;
-        const uint32_t c0 = fuse_count ? n_in_parts : 0u;
-        if (c0 < s->nOwned) {
-            if (halo)
-                LAUNCH(BENDY_K_GRID_BUILD, k2_count<true><<<cdiv(s->nOwned - c0, 256), 256, 0, st>>>(pos, c0, s->nOwned, ca));
-            else
-                LAUNCH(BENDY_K_GRID_BUILD, k2_count<false><<<cdiv(s->nOwned - c0, 256), 256, 0, st>>>(pos, c0, s->nOwned, ca));
-        }
-        return BENDY_OK;
-    };
-    if (overlap) {
-        cudaStream_t qx = s->side[0];  // free in strip mode (no circles)
-        if (int rc = run_local(PP, 0, s->d_part_start.p, s->d_part_cs.p, s->d_local.p, st, true, 0, nb, 1)) return rc;
-        if (int rc = count_unlinked()) return rc;
-        CK(cudaEventRecord(s->ev_main, st));
-        CK(cudaStreamWaitEvent(qx, s->ev_main, 0));
-        if (int rc = halo_exchange_nccl(qx)) return rc;
-        LAUNCH(BENDY_K_HALO, k_halo_clear<<<cdiv(s->ghost_cap, 256), 256, 0, qx>>>(s->d_send[0].p, s->d_send[1].p,
-                                                                                   s->d_send_cnt.p, s->ghost_cap));
-        CK(cudaEventRecord(s->ev_xchg, qx));
-        if (int rc = run_local(PP, 0, s->d_part_start.p, s->d_part_cs.p, s->d_local.p, st, true, nb, n_parts, 2)) return rc;
-        CK(cudaStreamWaitEvent(st, s->ev_xchg, 0));
-        LAUNCH(BENDY_K_GRID_BUILD, k2_count<false><<<cdiv(s->nP - s->nOwned, 256), 256, 0, st>>>(pos, s->nOwned, s->nP, ca));
-        goto after_halo;
-    }
-    if (int rc = run_local(PP, 0, s->d_part_start.p, s->d_part_cs.p, s->d_local.p, st, fuse_count, 0, n_parts, halo ? 1 : 0))
-        return rc;
-    if (int rc = run_global(PP, 0, s->d_global.p, st)) return rc;
-    if (int rc = count_unlinked()) return rc;
-    }
-    if (phase == PHASE_A) {
-        CK(cudaEventRecord(s->ev_phase_a, st));
-        return BENDY_OK;
-    }
-    if (halo && phase == PHASE_ALL)
-        if (int rc = halo_exchange_nccl(st)) return rc;
-phase_b:
-    if (halo) {  // my send buffers were consumed: reset them; then the received ghosts join the histogram
-        LAUNCH(BENDY_K_HALO, k_halo_clear<<<cdiv(s->ghost_cap, 256), 256, 0, st>>>(s->d_send[0].p, s->d_send[1].p,
-                                                                                   s->d_send_cnt.p, s->ghost_cap));
-        LAUNCH(BENDY_K_GRID_BUILD, k2_count<false><<<cdiv(s->nP - s->nOwned, 256), 256, 0, st>>>(pos, s->nOwned, s->nP, ca));
-    }
-after_halo:
-    cudaStream_t qc = (branch && s->nC > 0) ? s->side[0] : st;
-    cudaStream_t qg = (branch && nPoly > 0) ? s->side[1] : st;
-    if (discs) {
-        if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->scan_fused_capacity * 85) {
-            // every scan CTA fits on the device at once (15% spare; side-branch kernels finish on their own)
-            LAUNCH(BENDY_K_GRID_BUILD, k2_scan_fused<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(
-                                           s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
-        } else {
-            LAUNCH(BENDY_K_GRID_BUILD, k2_tile_reduce<<<cdiv(s->n_scan_tiles, 8), 256, 0, st>>>(
-                                           s->d_cell_count.p, s->n_scan_tiles, s->d_tile_sum.p));
-            LAUNCH(BENDY_K_GRID_BUILD, k2_scan<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->d_tile_sum.p,
-                                                                                         s->d_cell_start.p));
-        }
-#define SCATTER(ID, AG)                                                                                              \
-    LAUNCH(BENDY_K_GRID_BUILD, k2_scatter<ID, AG><<<cdiv(s->nP, 256), 256, 0, st>>>(                                  \
-                                   pos, s->nP, prm, s->n_cells, s->d_cell_start.p, s->d_scan_barrier.p,            \
-                                   s->d_sorted_pos.p, s->d_slot_of.p,                                                \
-                                   s->d_sorted_id.p))
-        if (K && s->scatter_agg)
-            SCATTER(true, true);
-        else if (K)
-            SCATTER(true, false);
-        else if (s->scatter_agg)
-            SCATTER(false, true);
-        else
-            SCATTER(false, false);
-#undef SCATTER
-    }
-    // ---- join: the collision phase needs all three worlds
-    if (branch) {
-        if (qc != st) {
-            if (!circ_joined) CK(cudaEventRecord(s->ev_join[0], qc));
-            CK(cudaStreamWaitEvent(st, s->ev_join[0], 0));
-        }
-        if (qg != st) {
-            CK(cudaEventRecord(s->ev_join[1], qg));
-            CK(cudaStreamWaitEvent(st, s->ev_join[1], 0));
-        }
-    }
-    K4Args k4{pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_center.p, s->d_poly_box.p, s->d_poly_tiles.p,
-              s->d_poly_static.p};
-    K1Args k1{pos,         s->d_prev.p,    s->accel_pending ? s->d_accel.p : nullptr, dk,
-              s->d_crad.p, s->d_gstatic.p, s->nP, s->nC, s->N};
-    const bool acc = s->accel_pending;
-    if (discs) {
-        // narrowphase + polygon contact + bounds + integrate for the free particles, fused
-        K2Args a{pos,     s->d_prev.p,   dk,    s->d_slot_of.p, s->d_sorted_id.p, s->d_sorted_pos.p, s->d_cell_start.p, s->n_cells,
-                 s->nP,   s->nOwned,     s->nC, s->d_crad.p,             s->d_circ_tile_count.p,  s->d_circ_tile_ids.p,
-                 s->d_circ_acc.p, s->d_circ_snap.p};
-        const uint32_t blocks = cdiv(s->nOwned, 128);
-        if (K && contact)
-            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<true, true><<<blocks, 128, 0, st>>>(a, k4, prm));
-        else if (K)
-            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<true, false><<<blocks, 128, 0, st>>>(a, k4, prm));
-        else if (contact)
-            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<false, true><<<blocks, 128, 0, st>>>(a, k4, prm));
-        else
-            LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<false, false><<<blocks, 128, 0, st>>>(a, k4, prm));
-        // tails: circles (apply + bounds + integrate) and polygon points (bounds + integrate), each
-        // behind the narrowphase on its own branch
-        if (branch && (qc != st || qg != st)) CK(cudaEventRecord(s->ev_main, st));
-        if (s->nC) {
-            if (qc != st) CK(cudaStreamWaitEvent(qc, s->ev_main, 0));
-            const uint32_t blocks_c = cdiv(s->nC, 128);
-#define CTAIL(A, KK)                                                                                         \
-    LAUNCH(BENDY_K_CIRCLES, k_circle_tail<A, KK, true><<<blocks_c, 128, 0, qc>>>(k1, s->d_circ_acc.p,        \
-                                                                                 s->d_circ_tile_count.p,   \
-                                                                                 s->n_circ_tiles, prm))
-            if (acc && K)
-                CTAIL(true, true);
-            else if (acc)
-                CTAIL(true, false);
-            else if (K)
-                CTAIL(false, true);
-            else
-                CTAIL(false, false);
-#undef CTAIL
-        }
-        if (s->nG) {
-            if (qg != st) CK(cudaStreamWaitEvent(qg, s->ev_main, 0));
-            const uint32_t first = s->nP + s->nC, n = s->nG, blocks_g = cdiv(n, 256);
-            if (acc && K)
-                LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, true><<<blocks_g, 256, 0, qg>>>(k1, first, n, prm));
-            else if (acc)
-                LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, false><<<blocks_g, 256, 0, qg>>>(k1, first, n, prm));
-            else if (K)
-                LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, true><<<blocks_g, 256, 0, qg>>>(k1, first, n, prm));
-            else
-                LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, false><<<blocks_g, 256, 0, qg>>>(k1, first, n, prm));
-        }
-        return BENDY_OK;
-    }
-    if (contact) {
-        if (K)
-            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<true><<<cdiv(s->nP, 128), 128, 0, st>>>(pos, dk, s->nP, k4, prm));
-        else
-            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<false><<<cdiv(s->nP, 128), 128, 0, st>>>(pos, dk, s->nP, k4, prm));
-    }
-    // ---- solve_boundary_collisions + update_positions (solver.rs:113-114), gravity fused: all points
-    {
-        uint32_t blocks = cdiv(s->Npad / 2, 256);
-        if (blocks) {
-            if (acc && K)
-                LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, true><<<blocks, 256, 0, st>>>(k1, prm));
-            else if (acc)
-                LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, false><<<blocks, 256, 0, st>>>(k1, prm));
-            else if (K)
-                LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, true><<<blocks, 256, 0, st>>>(k1, prm));
-            else
-                LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, false><<<blocks, 256, 0, st>>>(k1, prm));
-        }
-        // the next substep's circle / polygon chains must see the integrated state
-        if (branch) {
-            CK(cudaEventRecord(s->ev_main, st));
-            if (qc != st) CK(cudaStreamWaitEvent(qc, s->ev_main, 0));
-            if (qg != st) CK(cudaStreamWaitEvent(qg, s->ev_main, 0));
-        }
+               k_circles_exact<<<1, 1024, smem, c.qc>>>(cpos, s->d_crad.p, s->nC, smem ? 1 : 0, s->d_flags.p + 1));
     }
     return BENDY_OK;
+}
+
+// histogram (+ halo packing) of the owned discs the link kernel did not cover
+int Ops::launch_count_unlinked(const SubstepCtx &c) {
+    if (!c.discs) return BENDY_OK;
+    const uint32_t c0 = c.fuse_count ? c.n_in_parts : 0u;
+    if (c0 >= s->nOwned) return BENDY_OK;
+    if (c.halo)
+        LAUNCH(BENDY_K_GRID_BUILD, k2_count<true><<<cdiv(s->nOwned - c0, 256), 256, 0, c.st>>>(c.pos, c0, s->nOwned, c.ca));
+    else
+        LAUNCH(BENDY_K_GRID_BUILD, k2_count<false><<<cdiv(s->nOwned - c0, 256), 256, 0, c.st>>>(c.pos, c0, s->nOwned, c.ca));
+    return BENDY_OK;
+}
+
+// strips: my send buffers were consumed -> reset them; the received ghosts join the histogram
+int Ops::launch_halo_receive(const SubstepCtx &c, cudaStream_t q_clear) {
+    LAUNCH(BENDY_K_HALO, k_halo_clear<<<cdiv(s->ghost_cap, 256), 256, 0, q_clear>>>(s->d_send[0].p, s->d_send[1].p,
+                                                                                    s->d_send_cnt.p, s->ghost_cap));
+    if (q_clear != c.st) {
+        CK(cudaEventRecord(s->ev_xchg, q_clear));
+        CK(cudaStreamWaitEvent(c.st, s->ev_xchg, 0));
+    }
+    LAUNCH(BENDY_K_GRID_BUILD,
+           k2_count<false><<<cdiv(s->nP - s->nOwned, 256), 256, 0, c.st>>>(c.pos, s->nOwned, s->nP, c.ca));
+    return BENDY_OK;
+}
+
+// particle links (solver.rs:144-146) with the fused histogram; in strip mode also the halo packing.
+// *ghosts_done is set when the exchange AND the ghost histogram were already issued (overlap path).
+int Ops::launch_particle_links(const SubstepCtx &c, int phase, bool *ghosts_done) {
+    const LinkPlan &P = s->plan_p;
+    const uint32_t n_parts = P.n_parts(), nb = P.n_priority_parts;
+    *ghosts_done = false;
+    // Strips, graph mode, opt-in (BENDY_HALO_OVERLAP=1): the partitions of the bodies near the halo
+    // bands run first, their discs are packed, and the NCCL exchange proceeds on a side stream while
+    // the interior partitions are relaxed.  Measured on 8 x B200 (C5, 2M discs per rank) the split
+    // costs more than the exchange it hides (166 vs 153 us per substep), hence off by default.
+    const bool overlap = s->halo_overlap && c.halo && phase == PHASE_ALL && c.branch && c.fuse_count && s->nccl_comm &&
+                         nb > 0 && nb < n_parts;
+    if (overlap) {
+        cudaStream_t qx = s->side[0];  // free in strip mode (no circles)
+        if (int rc = launch_links_local(c, c.st, 0, nb, 1)) return rc;
+        if (int rc = launch_count_unlinked(c)) return rc;
+        CK(cudaEventRecord(s->ev_main, c.st));
+        CK(cudaStreamWaitEvent(qx, s->ev_main, 0));
+        if (int rc = halo_exchange_nccl(qx)) return rc;
+        if (int rc = launch_links_local(c, c.st, nb, n_parts, 2)) return rc;
+        if (int rc = launch_halo_receive(c, qx)) return rc;
+        *ghosts_done = true;
+        return BENDY_OK;
+    }
+    if (int rc = launch_links_local(c, c.st, 0, n_parts, c.halo ? 1 : 0)) return rc;
+    if (int rc = launch_links_global(c, c.st)) return rc;
+    return launch_count_unlinked(c);
+}
+
+// K2 grid build: exclusive scan of the cell histogram, then the counting-sort scatter
+int Ops::launch_grid_build(const SubstepCtx &c) {
+    if (!c.discs) return BENDY_OK;
+    cudaStream_t st = c.st;
+    if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->scan_fused_capacity * 85) {
+        // every scan CTA fits on the device at once (15% spare; side-branch kernels finish on their own)
+        LAUNCH(BENDY_K_GRID_BUILD, k2_scan_fused<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(
+                                       s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
+    } else {
+        LAUNCH(BENDY_K_GRID_BUILD,
+               k2_tile_reduce<<<cdiv(s->n_scan_tiles, 8), 256, 0, st>>>(s->d_cell_count.p, s->n_scan_tiles, s->d_tile_sum.p));
+        LAUNCH(BENDY_K_GRID_BUILD,
+               k2_scan<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p));
+    }
+#define SCATTER(ID, AG)                                                                                            \
+    LAUNCH(BENDY_K_GRID_BUILD, k2_scatter<ID, AG><<<cdiv(s->nP, 256), 256, 0, st>>>(                                \
+                                   c.pos, s->nP, c.prm, s->n_cells, s->d_cell_start.p, s->d_scan_barrier.p,       \
+                                   s->d_sorted_pos.p, s->d_slot_of.p, s->d_sorted_id.p))
+    if (c.K && s->scatter_agg)
+        SCATTER(true, true);
+    else if (c.K)
+        SCATTER(true, false);
+    else if (s->scatter_agg)
+        SCATTER(false, true);
+    else
+        SCATTER(false, false);
+#undef SCATTER
+    return BENDY_OK;
+}
+
+// disc grid on: narrowphase + polygon contact + bounds + integrate for the free particles in one
+// launch; then the tails (circles: apply + bounds + integrate; polygon points: bounds + integrate),
+// each behind the narrowphase on its own branch
+int Ops::launch_collide_integrate_discs(const SubstepCtx &c) {
+    cudaStream_t st = c.st;
+    K2Args a{c.pos,    s->d_prev.p, c.dk,  s->d_slot_of.p, s->d_sorted_id.p,       s->d_sorted_pos.p,    s->d_cell_start.p, s->n_cells,
+             s->nP,    s->nOwned,   s->nC, s->d_crad.p,    s->d_circ_tile_count.p, s->d_circ_tile_ids.p, s->d_circ_acc.p,
+             s->d_circ_snap.p};
+    const uint32_t blocks = cdiv(s->nOwned, 128);
+    if (c.K && c.contact)
+        LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<true, true><<<blocks, 128, 0, st>>>(a, c.k4, c.prm));
+    else if (c.K)
+        LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<true, false><<<blocks, 128, 0, st>>>(a, c.k4, c.prm));
+    else if (c.contact)
+        LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<false, true><<<blocks, 128, 0, st>>>(a, c.k4, c.prm));
+    else
+        LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<false, false><<<blocks, 128, 0, st>>>(a, c.k4, c.prm));
+    if (c.branch && (c.qc != st || c.qg != st)) CK(cudaEventRecord(s->ev_main, st));
+    if (s->nC) {
+        if (c.qc != st) CK(cudaStreamWaitEvent(c.qc, s->ev_main, 0));
+        const uint32_t blocks_c = cdiv(s->nC, 128);
+#define CTAIL(A, KK)                                                                                            \
+    LAUNCH(BENDY_K_CIRCLES, k_circle_tail<A, KK, true><<<blocks_c, 128, 0, c.qc>>>(c.k1, s->d_circ_acc.p,       \
+                                                                                   s->d_circ_tile_count.p,     \
+                                                                                   s->n_circ_tiles, c.prm))
+        if (c.acc && c.K)
+            CTAIL(true, true);
+        else if (c.acc)
+            CTAIL(true, false);
+        else if (c.K)
+            CTAIL(false, true);
+        else
+            CTAIL(false, false);
+#undef CTAIL
+    }
+    if (s->nG) {
+        if (c.qg != st) CK(cudaStreamWaitEvent(c.qg, s->ev_main, 0));
+        const uint32_t first = s->nP + s->nC, n = s->nG, blocks_g = cdiv(n, 256);
+        if (c.acc && c.K)
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, true><<<blocks_g, 256, 0, c.qg>>>(c.k1, first, n, c.prm));
+        else if (c.acc)
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, false><<<blocks_g, 256, 0, c.qg>>>(c.k1, first, n, c.prm));
+        else if (c.K)
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, true><<<blocks_g, 256, 0, c.qg>>>(c.k1, first, n, c.prm));
+        else
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, false><<<blocks_g, 256, 0, c.qg>>>(c.k1, first, n, c.prm));
+    }
+    return BENDY_OK;
+}
+
+// disc grid off (reference semantics for free particles): optional particle-polygon contact, then
+// solve_boundary_collisions + update_positions (solver.rs:113-114) for ALL points in one launch
+int Ops::launch_collide_integrate_plain(const SubstepCtx &c) {
+    cudaStream_t st = c.st;
+    if (c.contact) {
+        if (c.K)
+            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<true><<<cdiv(s->nP, 128), 128, 0, st>>>(c.pos, c.dk, s->nP, c.k4, c.prm));
+        else
+            LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_contact<false><<<cdiv(s->nP, 128), 128, 0, st>>>(c.pos, c.dk, s->nP, c.k4, c.prm));
+    }
+    const uint32_t blocks = cdiv(s->Npad / 2, 256);
+    if (blocks) {
+        if (c.acc && c.K)
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, true><<<blocks, 256, 0, st>>>(c.k1, c.prm));
+        else if (c.acc)
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate<true, false><<<blocks, 256, 0, st>>>(c.k1, c.prm));
+        else if (c.K)
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, true><<<blocks, 256, 0, st>>>(c.k1, c.prm));
+        else
+            LAUNCH(BENDY_K_INTEGRATE, k1_integrate<false, false><<<blocks, 256, 0, st>>>(c.k1, c.prm));
+    }
+    if (c.branch) {  // the next substep's circle / polygon chains must see the integrated state
+        CK(cudaEventRecord(s->ev_main, st));
+        if (c.qc != st) CK(cudaStreamWaitEvent(c.qc, s->ev_main, 0));
+        if (c.qg != st) CK(cudaStreamWaitEvent(c.qg, s->ev_main, 0));
+    }
+    return BENDY_OK;
+}
+
+// phase: PHASE_ALL = the whole substep (NCCL exchange in-stream); PHASE_A = up to the halo packing;
+// PHASE_B = from the ghost histogram on (bendy_update_group moves the halo between A and B).
+int Ops::launch_substep(int phase) {
+    SubstepCtx c = make_ctx();
+    bool ghosts_done = false;
+    if (phase != PHASE_B) {
+        if (int rc = launch_polygon_chain(c)) return rc;
+        if (int rc = launch_circle_chain(c)) return rc;
+        if (int rc = launch_particle_links(c, phase, &ghosts_done)) return rc;
+        if (phase == PHASE_A) {
+            CK(cudaEventRecord(s->ev_phase_a, c.st));
+            return BENDY_OK;
+        }
+        if (c.halo && !ghosts_done)
+            if (int rc = halo_exchange_nccl(c.st)) return rc;
+    }
+    if (c.halo && !ghosts_done)
+        if (int rc = launch_halo_receive(c, c.st)) return rc;
+    if (int rc = launch_grid_build(c)) return rc;
+    // ---- join: the collision phase needs all three worlds
+    if (c.branch) {
+        if (c.qc != c.st) {
+            if (!c.circ_joined) CK(cudaEventRecord(s->ev_join[0], c.qc));
+            CK(cudaStreamWaitEvent(c.st, s->ev_join[0], 0));
+        }
+        if (c.qg != c.st) {
+            CK(cudaEventRecord(s->ev_join[1], c.qg));
+            CK(cudaStreamWaitEvent(c.st, s->ev_join[1], 0));
+        }
+    }
+    return c.discs ? launch_collide_integrate_discs(c) : launch_collide_integrate_plain(c);
 }
 
 int Ops::build_graph(uint32_t substeps) {
