@@ -168,6 +168,7 @@ struct bendy_solver {
     bool scatter_agg = false;   // BENDY_SCATTER_AGG
     bool halo_overlap = false;  // BENDY_HALO_OVERLAP
     bool small_scene = true;    // BENDY_SMALL_SCENE=0 forces the multi-kernel path for tiny scenes
+    int pdl = 0;                // BENDY_PDL: 1 = programmatic dependent launch for links/scan/scatter, 2 = + narrowphase
     DevBuf<float2> d_sorted_pos;
     DevBuf<uint32_t> d_circ_tile_count, d_circ_tile_ids;
     uint32_t n_scan_tiles = 0, n_circ_tiles = 0;
@@ -697,6 +698,24 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
     return BENDY_OK;
 }
 
+// <<<grid, block, smem, q>>> with the programmatic-stream-serialisation attribute when `pdl` is set: the
+// kernel may become resident while its stream predecessor drains and orders itself with pdl_wait()
+template <typename... KArgs, typename... Args>
+static void launch_k(bool pdl, void (*kern)(KArgs...), uint32_t grid, uint32_t block, size_t smem, cudaStream_t q,
+                     Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = q;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);  // errors surface through cudaGetLastError() in launch()
+}
+
 #define LAUNCH(cls, ...)                                         \
     do {                                                         \
         int _rc = launch((cls), [&]() { __VA_ARGS__; });         \
@@ -789,18 +808,22 @@ int Ops::launch_links_local(const SubstepCtx &c, cudaStream_t q, uint32_t p0, ui
     float2 *pos = c.pos;
     const float *dk = c.dk;
     const K3CountArgs &ca = c.ca;
+    const bool pdl = s->pdl > 0;
+#define K3L(HK, FC, HM) \
+    LAUNCH(BENDY_K_LINKS_LOCAL, launch_k(pdl, k3_links_local<HK, FC, HM>, np, T, smem, q, pos, dk, 0u, ps, cs, ll, C, ca, p0))
     if (c.fuse_count && halo_mode == 1)  // strips: no inverse masses (checked in rebuild)
-        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 1><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+        K3L(false, true, 1);
     else if (c.fuse_count && halo_mode == 2)
-        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 2><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+        K3L(false, true, 2);
     else if (c.K && c.fuse_count)
-        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, true, 0><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+        K3L(true, true, 0);
     else if (c.K)
-        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<true, false, 0><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+        K3L(true, false, 0);
     else if (c.fuse_count)
-        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, true, 0><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+        K3L(false, true, 0);
     else
-        LAUNCH(BENDY_K_LINKS_LOCAL, k3_links_local<false, false, 0><<<np, T, smem, q>>>(pos, dk, 0, ps, cs, ll, C, ca, p0));
+        K3L(false, false, 0);
+#undef K3L
     return BENDY_OK;
 }
 
@@ -925,18 +948,18 @@ int Ops::launch_grid_build(const SubstepCtx &c) {
     cudaStream_t st = c.st;
     if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->scan_fused_capacity * 85) {
         // every scan CTA fits on the device at once (15% spare; side-branch kernels finish on their own)
-        LAUNCH(BENDY_K_GRID_BUILD, k2_scan_fused<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(
-                                       s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
+        LAUNCH(BENDY_K_GRID_BUILD, launch_k(s->pdl > 0, k2_scan_fused, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
+                                            s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
     } else {
         LAUNCH(BENDY_K_GRID_BUILD,
                k2_tile_reduce<<<cdiv(s->n_scan_tiles, 8), 256, 0, st>>>(s->d_cell_count.p, s->n_scan_tiles, s->d_tile_sum.p));
         LAUNCH(BENDY_K_GRID_BUILD,
                k2_scan<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p));
     }
-#define SCATTER(ID, AG)                                                                                            \
-    LAUNCH(BENDY_K_GRID_BUILD, k2_scatter<ID, AG><<<cdiv(s->nP, 256), 256, 0, st>>>(                                \
-                                   c.pos, s->nP, c.prm, s->n_cells, s->d_cell_start.p, s->d_scan_barrier.p,       \
-                                   s->d_sorted_pos.p, s->d_slot_of.p, s->d_sorted_id.p))
+#define SCATTER(ID, AG)                                                                                              \
+    LAUNCH(BENDY_K_GRID_BUILD, launch_k(s->pdl > 0, k2_scatter<ID, AG>, cdiv(s->nP, 256), 256, 0, st, c.pos, s->nP, c.prm, \
+                                        s->n_cells, s->d_cell_start.p, s->d_scan_barrier.p, s->d_sorted_pos.p,          \
+                                        s->d_slot_of.p, s->d_sorted_id.p))
     if (c.K && s->scatter_agg)
         SCATTER(true, true);
     else if (c.K)
@@ -958,14 +981,17 @@ int Ops::launch_collide_integrate_discs(const SubstepCtx &c) {
              s->nP,    s->nOwned,   s->nC, s->d_crad.p,    s->d_circ_tile_count.p, s->d_circ_tile_ids.p, s->d_circ_acc.p,
              s->d_circ_snap.p};
     const uint32_t blocks = cdiv(s->nOwned, 128);
+#define NARROW(HK, HP) \
+    LAUNCH(BENDY_K_NARROWPHASE, launch_k(s->pdl > 1, k2_narrow_contact_integrate<HK, HP>, blocks, 128, 0, st, a, c.k4, c.prm))
     if (c.K && c.contact)
-        LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<true, true><<<blocks, 128, 0, st>>>(a, c.k4, c.prm));
+        NARROW(true, true);
     else if (c.K)
-        LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<true, false><<<blocks, 128, 0, st>>>(a, c.k4, c.prm));
+        NARROW(true, false);
     else if (c.contact)
-        LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<false, true><<<blocks, 128, 0, st>>>(a, c.k4, c.prm));
+        NARROW(false, true);
     else
-        LAUNCH(BENDY_K_NARROWPHASE, k2_narrow_contact_integrate<false, false><<<blocks, 128, 0, st>>>(a, c.k4, c.prm));
+        NARROW(false, false);
+#undef NARROW
     if (c.branch && (c.qc != st || c.qg != st)) CK(cudaEventRecord(s->ev_main, st));
     if (s->nC) {
         if (c.qc != st) CK(cudaStreamWaitEvent(c.qc, s->ev_main, 0));
@@ -1216,6 +1242,7 @@ bendy_solver *bendy_create(int device) {
     if (const char *v = getenv("BENDY_SCATTER_AGG")) s->scatter_agg = atoi(v) != 0;
     if (const char *v = getenv("BENDY_HALO_OVERLAP")) s->halo_overlap = atoi(v) != 0;
     if (const char *v = getenv("BENDY_SMALL_SCENE")) s->small_scene = atoi(v) != 0;
+    if (const char *v = getenv("BENDY_PDL")) s->pdl = atoi(v);
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->side[0], cudaStreamNonBlocking)) != cudaSuccess ||
