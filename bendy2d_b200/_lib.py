@@ -59,6 +59,9 @@ def signatures():
         "bendy_clone": (vp, [vp]),
         "bendy_last_error": (C.c_char_p, [vp]),
         "bendy_abi_version": (i, []),
+        "bendy_save_snapshot": (i, [vp, C.c_char_p]),
+        "bendy_load_snapshot": (vp, [C.c_char_p, i]),
+        "bendy_get_last_update_args": (i, [vp, f32p, intp]),
         "bendy_add_particles": (i, [vp, f32p, sz]),
         "bendy_add_circles": (i, [vp, f32p, f32p, f32p, f32p, sz]),
         "bendy_add_polygon": (i, [vp, f32p, f32p, f32p, sz, u32p, f32p, sz, i, fl, fl]),

@@ -137,6 +137,8 @@ struct bendy_solver {
     std::vector<float> gl_len;
     bool any_acc = false;  // some circle / polygon point was added with acc != 0
 
+    float last_args[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // dt, gravity, bounds of the last update()
+    bool have_last_args = false;
     uint16_t sub_steps = 1;
     float particle_radius = 0.f;
     float grid_cell = 0.f;
@@ -168,7 +170,9 @@ struct bendy_solver {
     bool scatter_agg = false;   // BENDY_SCATTER_AGG
     bool halo_overlap = false;  // BENDY_HALO_OVERLAP
     bool small_scene = true;    // BENDY_SMALL_SCENE=0 forces the multi-kernel path for tiny scenes
-    int pdl = 0;                // BENDY_PDL: 1 = programmatic dependent launch for links/scan/scatter, 2 = + narrowphase
+    int pdl = 2;                // BENDY_PDL: 0 = off, 1 = programmatic dependent launch for links/scan/scatter,
+                                // 2 = + narrowphase (default; not yet used on the NCCL strip path: BENDY_PDL_NCCL=1)
+    bool pdl_nccl = false;
     DevBuf<float2> d_sorted_pos;
     DevBuf<uint32_t> d_circ_tile_count, d_circ_tile_ids;
     uint32_t n_scan_tiles = 0, n_circ_tiles = 0;
@@ -242,6 +246,7 @@ struct SubstepCtx {
     float2 *pos;
     const float *dk;
     bool K, discs, contact, halo, branch, acc, fuse_count;
+    int pdl;  // programmatic dependent launch level for the particle chain (0 = plain launches)
     bool circ_joined;  // the circle chain's join event was already recorded (after the bins)
     uint32_t nPoly, n_in_parts;
     K3CountArgs ca;
@@ -779,6 +784,7 @@ SubstepCtx Ops::make_ctx() {
     c.contact = s->polygon_contact && c.nPoly && s->nP;
     c.halo = s->halo_on && c.discs && s->ghost_cap > 0;
     c.acc = s->accel_pending;
+    c.pdl = (s->nccl_comm && !s->pdl_nccl) ? 0 : s->pdl;
     c.ca = K3CountArgs{c.prm,
                        s->n_cells,
                        s->d_cell_count.p,
@@ -808,7 +814,7 @@ int Ops::launch_links_local(const SubstepCtx &c, cudaStream_t q, uint32_t p0, ui
     float2 *pos = c.pos;
     const float *dk = c.dk;
     const K3CountArgs &ca = c.ca;
-    const bool pdl = s->pdl > 0;
+    const bool pdl = c.pdl > 0;
 #define K3L(HK, FC, HM) \
     LAUNCH(BENDY_K_LINKS_LOCAL, launch_k(pdl, k3_links_local<HK, FC, HM>, np, T, smem, q, pos, dk, 0u, ps, cs, ll, C, ca, p0))
     if (c.fuse_count && halo_mode == 1)  // strips: no inverse masses (checked in rebuild)
@@ -896,7 +902,8 @@ int Ops::launch_count_unlinked(const SubstepCtx &c) {
     if (c.halo)
         LAUNCH(BENDY_K_GRID_BUILD, k2_count<true><<<cdiv(s->nOwned - c0, 256), 256, 0, c.st>>>(c.pos, c0, s->nOwned, c.ca));
     else
-        LAUNCH(BENDY_K_GRID_BUILD, k2_count<false><<<cdiv(s->nOwned - c0, 256), 256, 0, c.st>>>(c.pos, c0, s->nOwned, c.ca));
+        LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_count<false>, cdiv(s->nOwned - c0, 256), 256, 0, c.st, c.pos, c0,
+                                            s->nOwned, c.ca));
     return BENDY_OK;
 }
 
@@ -948,7 +955,7 @@ int Ops::launch_grid_build(const SubstepCtx &c) {
     cudaStream_t st = c.st;
     if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->scan_fused_capacity * 85) {
         // every scan CTA fits on the device at once (15% spare; side-branch kernels finish on their own)
-        LAUNCH(BENDY_K_GRID_BUILD, launch_k(s->pdl > 0, k2_scan_fused, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
+        LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan_fused, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
                                             s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
     } else {
         LAUNCH(BENDY_K_GRID_BUILD,
@@ -957,7 +964,7 @@ int Ops::launch_grid_build(const SubstepCtx &c) {
                k2_scan<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p));
     }
 #define SCATTER(ID, AG)                                                                                              \
-    LAUNCH(BENDY_K_GRID_BUILD, launch_k(s->pdl > 0, k2_scatter<ID, AG>, cdiv(s->nP, 256), 256, 0, st, c.pos, s->nP, c.prm, \
+    LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scatter<ID, AG>, cdiv(s->nP, 256), 256, 0, st, c.pos, s->nP, c.prm, \
                                         s->n_cells, s->d_cell_start.p, s->d_scan_barrier.p, s->d_sorted_pos.p,          \
                                         s->d_slot_of.p, s->d_sorted_id.p))
     if (c.K && s->scatter_agg)
@@ -982,7 +989,7 @@ int Ops::launch_collide_integrate_discs(const SubstepCtx &c) {
              s->d_circ_snap.p};
     const uint32_t blocks = cdiv(s->nOwned, 128);
 #define NARROW(HK, HP) \
-    LAUNCH(BENDY_K_NARROWPHASE, launch_k(s->pdl > 1, k2_narrow_contact_integrate<HK, HP>, blocks, 128, 0, st, a, c.k4, c.prm))
+    LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_contact_integrate<HK, HP>, blocks, 128, 0, st, a, c.k4, c.prm))
     if (c.K && c.contact)
         NARROW(true, true);
     else if (c.K)
@@ -1243,10 +1250,20 @@ bendy_solver *bendy_create(int device) {
     if (const char *v = getenv("BENDY_HALO_OVERLAP")) s->halo_overlap = atoi(v) != 0;
     if (const char *v = getenv("BENDY_SMALL_SCENE")) s->small_scene = atoi(v) != 0;
     if (const char *v = getenv("BENDY_PDL")) s->pdl = atoi(v);
-    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+    if (const char *v = getenv("BENDY_PDL_NCCL")) s->pdl_nccl = atoi(v) != 0;
+    // BENDY_SIDE_PRIORITY=1: the circle / polygon branches get the highest stream priority, so their few
+    // CTAs are dispatched ahead of the queued CTAs of the particle chain (kernel nodes keep the priority
+    // of the stream they were captured on)
+    int prio_side = 0;
+    if ((e = cudaSetDevice(device)) == cudaSuccess) {
+        const char *v = getenv("BENDY_SIDE_PRIORITY");
+        int least = 0, greatest = 0;
+        if (v && atoi(v) != 0 && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) prio_side = greatest;
+    }
+    if (e != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&s->side[0], cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&s->side[1], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&s->side[0], cudaStreamNonBlocking, prio_side)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&s->side[1], cudaStreamNonBlocking, prio_side)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&s->ev_join[0], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&s->ev_join[1], cudaEventDisableTiming)) != cudaSuccess ||
@@ -1275,10 +1292,185 @@ bendy_solver *bendy_clone(bendy_solver *s) {
     c->gl_ab = s->gl_ab, c->gl_len = s->gl_len, c->any_acc = s->any_acc;
     c->sub_steps = s->sub_steps, c->particle_radius = s->particle_radius, c->grid_cell = s->grid_cell;
     c->polygon_contact = s->polygon_contact, c->plan_params = s->plan_params;
+    memcpy(c->last_args, s->last_args, sizeof c->last_args), c->have_last_args = s->have_last_args;
     // strip configuration travels too; the transport (NCCL communicator / local peers) does not
     c->halo_on = s->halo_on, c->ghost_cap = s->ghost_cap, c->halo_xl = s->halo_xl, c->halo_xr = s->halo_xr;
     c->stray_xl = s->stray_xl, c->stray_xr = s->stray_xr, c->win_x0 = s->win_x0, c->win_x1 = s->win_x1;
     return c;
+}
+
+// ---- snapshot: the whole scene as one flat little-endian file of 4-byte words -------------------
+// (the reference's only checkpoint is #[derive(Clone)], solver.rs:19; this is the same state on disk,
+// so a parity failure can be replayed elsewhere: bendy2d_b200/snapshot.py reads it with numpy)
+//   magic "B2DSNAP1" | u32 version, sub_steps | f32 particle_radius, grid_cell | u32 polygon_contact,
+//   pack_points, max_points, has_last_update | f32 last dt, gx, gy, bx, by, bw, bh, 0 |
+//   u64 nP, nC, nPoly, nG, nPL, nCL, nGL, has_particle_k, has_circle_k |
+//   p_pos[2nP] p_prev[2nP] (p_k[nP]) | c_pos c_prev c_acc[2nC each] c_rad[nC] (c_k[nC]) |
+//   pl_ab[2nPL] pl_len[nPL] | cl_ab[2nCL] cl_len[nCL] |
+//   per polygon: u32 start, nv, link_start, nl, is_static, f32 cx, cy | g_pos g_prev g_acc[2nG each] |
+//   gl_ab[2nGL] gl_len[nGL]
+extern "C++" {
+namespace {
+const char kSnapMagic[8] = {'B', '2', 'D', 'S', 'N', 'A', 'P', '1'};
+struct SnapHeader {
+    char magic[8];
+    uint32_t version, sub_steps;
+    float particle_radius, grid_cell;
+    uint32_t polygon_contact, pack_points, max_points, has_last;
+    float last[8];
+    uint64_t n[9];  // nP, nC, nPoly, nG, nPL, nCL, nGL, has_pk, has_ck
+};
+static_assert(sizeof(SnapHeader) == 8 + 8 + 8 + 16 + 32 + 72, "snapshot header layout");
+struct SnapPoly {
+    uint32_t start, nv, link_start, nl, is_static;
+    float cx, cy;
+};
+template <typename T>
+bool put(FILE *f, const std::vector<T> &v) {
+    return v.empty() || fwrite(v.data(), sizeof(T), v.size(), f) == v.size();
+}
+template <typename T>
+bool get(FILE *f, std::vector<T> &v, uint64_t n) {
+    v.resize(n);
+    return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
+}
+}  // namespace
+}  // extern "C++"
+
+int bendy_save_snapshot(bendy_solver *s, const char *path) {
+    NEED(s);
+    OPS;
+    if (!path) return ops.fail(BENDY_ERR_ARG, "bendy_save_snapshot: null path");
+    if (s->sticky != BENDY_OK) return ops.fail(s->sticky, s->err);
+    if (!s->host_valid) {
+        if (int rc = ops.bind()) return rc;
+        if (int rc = ops.pull()) return rc;
+    }
+    SnapHeader h{};
+    memcpy(h.magic, kSnapMagic, 8);
+    h.version = 1, h.sub_steps = s->sub_steps;
+    h.particle_radius = s->particle_radius, h.grid_cell = s->grid_cell;
+    h.polygon_contact = s->polygon_contact, h.pack_points = s->plan_params.pack_points;
+    h.max_points = s->plan_params.max_points, h.has_last = s->have_last_args;
+    for (int i = 0; i < 7; i++) h.last[i] = s->last_args[i];
+    const uint64_t n[9] = {s->p_pos.size(), s->c_pos.size(), s->polys.size(), s->g_pos.size(), s->pl_len.size(),
+                           s->cl.size(),    s->gl_len.size(), s->p_k.empty() ? 0u : 1u, s->c_k.empty() ? 0u : 1u};
+    for (int i = 0; i < 9; i++) h.n[i] = n[i];
+    std::vector<uint32_t> cl_ab;
+    std::vector<float> cl_len;
+    for (const GlobalLink &l : s->cl) cl_ab.push_back(l.a), cl_ab.push_back(l.b), cl_len.push_back(l.len);
+    std::vector<SnapPoly> polys;
+    for (const PolyHost &P : s->polys)
+        polys.push_back(SnapPoly{P.start, P.nv, P.link_start, P.nl, P.is_static ? 1u : 0u, P.center.x, P.center.y});
+    FILE *f = fopen(path, "wb");
+    if (!f) return ops.fail(BENDY_ERR_ARG, std::string("bendy_save_snapshot: cannot open ") + path);
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1 && put(f, s->p_pos) && put(f, s->p_prev) && put(f, s->p_k) &&
+              put(f, s->c_pos) && put(f, s->c_prev) && put(f, s->c_acc) && put(f, s->c_rad) && put(f, s->c_k) &&
+              put(f, s->pl_ab) && put(f, s->pl_len) && put(f, cl_ab) && put(f, cl_len) && put(f, polys) &&
+              put(f, s->g_pos) && put(f, s->g_prev) && put(f, s->g_acc) && put(f, s->gl_ab) && put(f, s->gl_len);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return ops.fail(BENDY_ERR_ARG, std::string("bendy_save_snapshot: short write to ") + path);
+    return BENDY_OK;
+}
+
+bendy_solver *bendy_load_snapshot(const char *path, int device) {
+    if (!path) {
+        g_last_error = "bendy_load_snapshot: null path";
+        return nullptr;
+    }
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        g_last_error = std::string("bendy_load_snapshot: cannot open ") + path;
+        return nullptr;
+    }
+    // the file is parsed and validated completely before a device is touched
+    std::unique_ptr<bendy_solver> t(new bendy_solver());
+    SnapHeader h{};
+    std::vector<uint32_t> cl_ab;
+    std::vector<float> cl_len;
+    std::vector<SnapPoly> polys;
+    const char *why = nullptr;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kSnapMagic, 8) != 0)
+        why = "not a bendy2d snapshot (bad magic)";
+    else if (h.version != 1)
+        why = "unsupported snapshot version";
+    else if (h.sub_steps == 0 || h.sub_steps > 0xFFFFu)
+        why = "corrupt header (sub_steps)";
+    else {
+        for (int i = 0; i < 7; i++)
+            if (h.n[i] > 0x7FFFFFF0ull) why = "corrupt header (counts)";
+    }
+    if (!why) {
+        const uint64_t nP = h.n[0], nC = h.n[1], nPoly = h.n[2], nG = h.n[3], nPL = h.n[4], nCL = h.n[5], nGL = h.n[6];
+        bool ok = get(f, t->p_pos, nP) && get(f, t->p_prev, nP) && get(f, t->p_k, h.n[7] ? nP : 0) &&
+                  get(f, t->c_pos, nC) && get(f, t->c_prev, nC) && get(f, t->c_acc, nC) && get(f, t->c_rad, nC) &&
+                  get(f, t->c_k, h.n[8] ? nC : 0) && get(f, t->pl_ab, 2 * nPL) && get(f, t->pl_len, nPL) &&
+                  get(f, cl_ab, 2 * nCL) && get(f, cl_len, nCL) && get(f, polys, nPoly) && get(f, t->g_pos, nG) &&
+                  get(f, t->g_prev, nG) && get(f, t->g_acc, nG) && get(f, t->gl_ab, 2 * nGL) && get(f, t->gl_len, nGL);
+        if (!ok)
+            why = "truncated snapshot";
+        else if (fgetc(f) != EOF)
+            why = "trailing bytes after the snapshot";
+        // the same index rules the add_* calls enforce (link.rs:19-21)
+        for (uint64_t k = 0; !why && k < nPL; k++)
+            if (!(t->pl_ab[2 * k] < t->pl_ab[2 * k + 1]) || !(t->pl_ab[2 * k + 1] < nP)) why = "particle link out of range";
+        for (uint64_t k = 0; !why && k < nCL; k++)
+            if (!(cl_ab[2 * k] < cl_ab[2 * k + 1]) || !(cl_ab[2 * k + 1] < nC)) why = "circle link out of range";
+        uint64_t pts = 0, lks = 0;
+        for (uint64_t k = 0; !why && k < nPoly; k++) {
+            const SnapPoly &P = polys[k];
+            if (P.start != pts || P.link_start != lks || P.nv == 0 || pts + P.nv > nG || lks + P.nl > nGL)
+                why = "polygon table inconsistent";
+            for (uint32_t l = 0; !why && l < P.nl; l++) {
+                const uint32_t a = t->gl_ab[2 * (lks + l)], b = t->gl_ab[2 * (lks + l) + 1];
+                if (!(a < b) || !(b < P.nv)) why = "polygon link out of range";
+            }
+            pts += P.nv, lks += P.nl;
+        }
+        if (!why && (pts != nG || lks != nGL)) why = "polygon table does not cover the polygon points";
+    }
+    fclose(f);
+    if (why) {
+        g_last_error = std::string("bendy_load_snapshot: ") + why + " (" + path + ")";
+        return nullptr;
+    }
+    bendy_solver *s = bendy_create(device);
+    if (!s) return nullptr;
+    s->p_pos.swap(t->p_pos), s->p_prev.swap(t->p_prev), s->p_k.swap(t->p_k);
+    s->c_pos.swap(t->c_pos), s->c_prev.swap(t->c_prev), s->c_acc.swap(t->c_acc), s->c_rad.swap(t->c_rad);
+    s->c_k.swap(t->c_k), s->pl_ab.swap(t->pl_ab), s->pl_len.swap(t->pl_len);
+    for (size_t k = 0; k < cl_len.size(); k++) s->cl.push_back(GlobalLink{cl_ab[2 * k], cl_ab[2 * k + 1], cl_len[k]});
+    for (const SnapPoly &P : polys) {
+        PolyHost H;
+        H.start = P.start, H.nv = P.nv, H.link_start = P.link_start, H.nl = P.nl, H.is_static = P.is_static != 0;
+        H.center = make_float2(P.cx, P.cy);
+        s->polys.push_back(H);
+    }
+    s->g_pos.swap(t->g_pos), s->g_prev.swap(t->g_prev), s->g_acc.swap(t->g_acc);
+    s->gl_ab.swap(t->gl_ab), s->gl_len.swap(t->gl_len);
+    for (const float2 &a : s->c_acc)
+        if (a.x != 0.f || a.y != 0.f) s->any_acc = true;
+    for (const PolyHost &P : s->polys)
+        for (uint32_t v = 0; v < P.nv && !P.is_static; v++)
+            if (s->g_acc[P.start + v].x != 0.f || s->g_acc[P.start + v].y != 0.f) s->any_acc = true;
+    s->sub_steps = (uint16_t)h.sub_steps;
+    s->particle_radius = h.particle_radius, s->grid_cell = h.grid_cell;
+    s->polygon_contact = h.polygon_contact != 0;
+    s->plan_params.pack_points = h.pack_points, s->plan_params.max_points = h.max_points;
+    s->have_last_args = h.has_last != 0;
+    for (int i = 0; i < 7; i++) s->last_args[i] = h.last[i];
+    return s;
+}
+
+int bendy_get_last_update_args(const bendy_solver *s, float *dt_g_bounds7, int *valid) {
+    NEED(s);
+    if (!dt_g_bounds7 || !valid) {
+        g_last_error = "bendy_get_last_update_args: null output";
+        return BENDY_ERR_ARG;
+    }
+    for (int i = 0; i < 7; i++) dt_g_bounds7[i] = s->last_args[i];
+    *valid = s->have_last_args ? 1 : 0;
+    return BENDY_OK;
 }
 
 // ---- scene construction --------------------------------------------------------------------
@@ -1410,6 +1602,9 @@ int bendy_update_n(bendy_solver *s, uint32_t n, float dt, float gx, float gy, fl
     if (int rc = ops.configure(delta, gx, gy, bx, by, bw, bh)) return rc;
     if (int rc = ops.enqueue_substeps(n)) return rc;
     s->host_valid = false;
+    const float args[7] = {dt, gx, gy, bx, by, bw, bh};
+    memcpy(s->last_args, args, sizeof args);
+    s->have_last_args = true;
     return BENDY_OK;
 }
 
@@ -1854,6 +2049,9 @@ int bendy_update_group(bendy_solver **group, int n, uint32_t n_updates, float dt
         float delta = dt * (1.0f / (float)s->sub_steps);
         if (int rc = ops.configure(delta, gx, gy, bx, by, bw, bh)) return rc;
         if (s->sub_steps != group[0]->sub_steps) return ops.fail(BENDY_ERR_ARG, "group members need equal sub_steps");
+        const float args[7] = {dt, gx, gy, bx, by, bw, bh};
+        memcpy(s->last_args, args, sizeof args);
+        s->have_last_args = true;
     }
     const uint32_t total = n_updates * group[0]->sub_steps;
     for (uint32_t step = 0; step < total; step++) {

@@ -9,6 +9,7 @@ the parity tests and bench.py.  All state lives on the GPU; there is no CPU path
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
@@ -205,6 +206,28 @@ class Solver:
         c.gravity, c.bounds = self.gravity.copy(), Bounds(self.bounds.pos.copy(), self.bounds.size.copy())
         c.bounds_active = self.bounds_active
         return c
+
+    # ---- snapshot (raw SoA snapshot / restore) ----------------------------------
+    def save_snapshot(self, path: str):
+        """The state `clone()` copies, as one flat file (format: bendy2d_b200/snapshot.py)."""
+        self._ck(self._L.bendy_save_snapshot(self._h, os.fsencode(path)))
+
+    @staticmethod
+    def load_snapshot(path: str, device: int = -1) -> "Solver":
+        """A new Solver that continues bit-identically to the one that was saved.  `gravity` and
+        `bounds` (per-call arguments of the C ABI) come back from the last update, if one ran."""
+        L = _lib.lib()
+        h = L.bendy_load_snapshot(os.fsencode(path), device)
+        if not h:
+            raise BendyError(-1, (L.bendy_last_error(None) or b"").decode() or "bendy_load_snapshot failed")
+        s = Solver(_handle=h)
+        last = np.zeros(7, np.float32)
+        valid = C.c_int(0)
+        s._ck(L.bendy_get_last_update_args(h, _fp(last), C.byref(valid)))
+        if valid.value:
+            s.gravity = last[1:3].copy()
+            s.bounds = Bounds(last[3:5].copy(), last[5:7].copy())
+        return s
 
     # ---- add_* (solver.rs:52-67) -------------------------------------------------------------
     def add_particle(self, pos):

@@ -48,6 +48,19 @@ void bendy_destroy(bendy_solver *s);
 bendy_solver *bendy_clone(bendy_solver *s);
 const char *bendy_last_error(const bendy_solver *s);
 int bendy_abi_version(void);
+/* The same state as bendy_clone, on disk (the reference has no file format, Clone at
+ * solver.rs:19 is its only checkpoint): every particle / circle / polygon point with pos, prev and pending
+ * acc, all links in insertion order, polygon tables, inverse-mass scales, sub_steps, particle radius, grid
+ * cell, polygon-contact switch, plan parameters and the arguments of the last update.  A flat file of
+ * little-endian 4-byte words (layout in bendy2d_b200/csrc/solver.cu and bendy2d_b200/snapshot.py); strip /
+ * halo configuration is not part of it.  A loaded solver continues bit-identically to the saved one.
+ * bendy_load_snapshot validates the whole file (sizes, link index rules of link.rs:19-21) before it
+ * touches a device and returns NULL on failure (bendy_last_error(NULL) has the reason). */
+int bendy_save_snapshot(bendy_solver *s, const char *path);
+bendy_solver *bendy_load_snapshot(const char *path, int device);
+/* dt, gravity x/y, bounds x/y/w/h of the most recent update (pub fields gravity / bounds of the reference's
+ * Solver, solver.rs:21-22, which this ABI takes per call); *valid = 0 when no update has run yet */
+int bendy_get_last_update_args(const bendy_solver *s, float *dt_g_bounds7, int *valid);
 
 /* ---------------------------------------------------------------- scene construction */
 /* Solver::add_particle (solver.rs:52-54) x n: Particle::new => prev=pos, acc=0 (particle.rs:12-18) */

@@ -33,6 +33,9 @@ extern "C" {
     pub fn bendy_clone(s: *mut bendy_solver) -> *mut bendy_solver;
     pub fn bendy_last_error(s: *const bendy_solver) -> *const c_char;
     pub fn bendy_abi_version() -> c_int;
+    pub fn bendy_save_snapshot(s: *mut bendy_solver, path: *const c_char) -> c_int;
+    pub fn bendy_load_snapshot(path: *const c_char, device: c_int) -> *mut bendy_solver;
+    pub fn bendy_get_last_update_args(s: *const bendy_solver, dt_g_bounds7: *mut c_float, valid: *mut c_int) -> c_int;
 
     pub fn bendy_add_particles(s: *mut bendy_solver, pos_xy: *const c_float, n: usize) -> c_int;
     pub fn bendy_add_circles(s: *mut bendy_solver, pos_xy: *const c_float, prev_xy: *const c_float,

@@ -66,6 +66,15 @@ int main(void) {
     rc |= bendy_update_group(grp, 1, 1, 0.01f, 0.f, 98.2f, 0.f, 0.f, 100.f, 100.f);
     rc |= bendy_plan_links(2, ab, 1, 0, 0, rank, perm, NULL, NULL, &info);
     {
+        float last[7];
+        int valid = 0;
+        bendy_solver *c3;
+        rc |= bendy_get_last_update_args(s, last, &valid);
+        rc |= bendy_save_snapshot(s, "/tmp/bendy_c_abi_check.snap");
+        c3 = bendy_load_snapshot("/tmp/bendy_c_abi_check.snap", -1);
+        if (c3) bendy_destroy(c3);
+    }
+    {
         bendy_solver *c2 = bendy_clone(s);
         if (c2) {
             rc |= bendy_halo_connect_local(s, c2) != BENDY_OK ? 0 : 0;

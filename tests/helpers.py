@@ -30,6 +30,68 @@ def oracle_from_scene(sc: scenes.Scene) -> bo.OracleSolver:
     return o
 
 
+def oracle_from_snapshot(snap, gravity=None, bounds=None) -> bo.OracleSolver:
+    """Replay a bendy2d_b200.snapshot.Snapshot into the CPU oracle (gravity / bounds default to the
+    arguments of the last update stored in the snapshot)."""
+    o = bo.OracleSolver()
+    last = snap.last_update
+    o.set_gravity(*(gravity if gravity is not None else last[1:3]))
+    o.set_bounds(*(bounds if bounds is not None else last[3:7]))
+    if len(snap.particles_pos):
+        o.add_particles(snap.particles_pos)
+        o.write_particles(snap.particles_pos, snap.particles_prev)
+    if len(snap.particle_links_len):
+        o.add_particle_links(snap.particle_links_ab, snap.particle_links_len)
+    for p, q, a, r in zip(snap.circles_pos, snap.circles_prev, snap.circles_acc, snap.circles_radius):
+        o.add_circle(p, float(r), q, (float(a[0]), float(a[1])))
+    for a, b, l in zip(snap.circle_links_ab[:, 0], snap.circle_links_ab[:, 1], snap.circle_links_len):
+        o.add_circle_link(int(a), int(b), float(l))
+    for k in range(snap.n_polygons):
+        pg = snap.polygon(k)
+        o.add_polygon(pg["pos"], pg["link_ab"], pg["link_len"], pg["is_static"], pg["center"], pg["prev"], pg["acc"])
+    o.set_sub_steps(snap.sub_steps)
+    o.set_particle_radius(snap.particle_radius)
+    o.set_polygon_contact(snap.polygon_contact)
+    if snap.particles_inv_mass is not None:
+        o.set_particle_inv_mass(0, snap.particles_inv_mass)
+    if snap.circles_inv_mass is not None:
+        o.set_circle_inv_mass(0, snap.circles_inv_mass)
+    return o
+
+
+def snapshot_from_scene(sc: scenes.Scene):
+    """The snapshot a freshly loaded Scene would produce (no update yet)."""
+    from bendy2d_b200.snapshot import Snapshot
+
+    s = Snapshot(sub_steps=sc.sub_steps, particle_radius=sc.particle_radius, polygon_contact=sc.polygon_contact)
+    s.particles_pos = np.ascontiguousarray(sc.particles, f32).reshape(-1, 2)
+    s.particles_prev = s.particles_pos.copy()
+    s.particle_links_ab = np.ascontiguousarray(sc.links_ab, np.uint32).reshape(-1, 2)
+    s.particle_links_len = np.ascontiguousarray(sc.links_len, f32)
+    s.circles_pos = np.ascontiguousarray(sc.circles_pos, f32).reshape(-1, 2)
+    s.circles_prev = s.circles_pos.copy()
+    s.circles_acc = np.zeros_like(s.circles_pos)
+    s.circles_radius = np.ascontiguousarray(sc.circles_r, f32)
+    starts, nvs, lstarts, nls, cens, pts_all, ab_all, ln_all = [], [], [], [], [], [], [], []
+    p0 = l0 = 0
+    for pts in sc.polygons:
+        ab, ln, cen = scenes.polygon_new_tables(pts)
+        starts.append(p0), nvs.append(len(pts)), lstarts.append(l0), nls.append(len(ln)), cens.append(cen)
+        pts_all.append(np.asarray(pts, f32)), ab_all.append(np.asarray(ab, np.uint32).reshape(-1, 2)), ln_all.append(ln)
+        p0, l0 = p0 + len(pts), l0 + len(ln)
+    if starts:
+        s.poly_start, s.poly_nv = np.array(starts, np.uint32), np.array(nvs, np.uint32)
+        s.poly_link_start, s.poly_nl = np.array(lstarts, np.uint32), np.array(nls, np.uint32)
+        s.poly_static = np.array(sc.polygons_static, bool)
+        s.poly_center = np.array(cens, f32).reshape(-1, 2)
+        s.poly_points_pos = np.concatenate(pts_all).astype(f32)
+        s.poly_points_prev = s.poly_points_pos.copy()
+        s.poly_points_acc = np.zeros_like(s.poly_points_pos)
+        s.poly_links_ab = np.concatenate(ab_all).astype(np.uint32)
+        s.poly_links_len = np.concatenate(ln_all).astype(f32)
+    return s
+
+
 def sync_schedule(gpu, o: bo.OracleSolver, sc: scenes.Scene):
     """Feed the oracle the GPU's schedule: link order, in-cell rank, grid."""
     if sc.n_links:
