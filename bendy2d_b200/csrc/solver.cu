@@ -170,8 +170,9 @@ struct bendy_solver {
     bool scatter_agg = false;   // BENDY_SCATTER_AGG
     bool halo_overlap = false;  // BENDY_HALO_OVERLAP
     bool small_scene = true;    // BENDY_SMALL_SCENE=0 forces the multi-kernel path for tiny scenes
-    int pdl = 2;                // BENDY_PDL: 0 = off, 1 = programmatic dependent launch for links/scan/scatter,
-                                // 2 = + narrowphase (default; not yet used on the NCCL strip path: BENDY_PDL_NCCL=1)
+    int pdl = 3;                // BENDY_PDL: 0 = off, 1 = programmatic dependent launch for links/scan/scatter,
+                                // 2 = + narrowphase, 3 = + the circle / polygon branches (default); not yet used
+                                // on the NCCL strip path (BENDY_PDL_NCCL=1)
     bool pdl_nccl = false;
     DevBuf<float2> d_sorted_pos;
     DevBuf<uint32_t> d_circ_tile_count, d_circ_tile_ids;
@@ -863,8 +864,8 @@ int Ops::launch_polygon_chain(const SubstepCtx &c) {
     PolyLinkArgs la{s->d_poly_link_start.p, s->d_poly_link_ab.p, s->d_poly_link_len.p};
     LAUNCH(BENDY_K_POLY_PREP, k_poly_prepare<<<cdiv(c.nPoly, 128), 128, 0, c.qg>>>(pts, pa, la, c.prm, bins ? 1 : 0));
     if (c.nPoly >= 2) {
-        LAUNCH(BENDY_K_POLY_CONTACT, k4_poly_pair_prescan<<<cdiv(c.nPoly, 128), 128, 0, c.qg>>>(pa, c.prm));
-        LAUNCH(BENDY_K_POLY_CONTACT, k_polygons_exact<<<1, 1024, 0, c.qg>>>(pts, pa, c.prm, s->n_poly_tiles));
+        LAUNCH(BENDY_K_POLY_CONTACT, launch_k(c.pdl > 2, k4_poly_pair_prescan, cdiv(c.nPoly, 128), 128, 0, c.qg, pa, c.prm));
+        LAUNCH(BENDY_K_POLY_CONTACT, launch_k(c.pdl > 2, k_polygons_exact, 1, 1024, 0, c.qg, pts, pa, c.prm, s->n_poly_tiles));
     }
     return BENDY_OK;
 }
@@ -878,9 +879,8 @@ int Ops::launch_circle_chain(SubstepCtx &c) {
     if (!s->cl.empty())
         LAUNCH(BENDY_K_LINKS_CIRCLE, k3_circle_links<<<1, 32, 0, c.qc>>>(cpos, s->d_crad.p, s->d_clinks.p, (uint32_t)s->cl.size()));
     if (c.discs && s->nC) {
-        LAUNCH(BENDY_K_CIRCLES, k2_circle_bin<<<cdiv(s->nC, 128), 128, 0, c.qc>>>(cpos, s->d_crad.p, s->nC, c.prm,
-                                                                                   s->d_circ_tile_count.p,
-                                                                                   s->d_circ_tile_ids.p, s->d_circ_snap.p));
+        LAUNCH(BENDY_K_CIRCLES, launch_k(c.pdl > 2, k2_circle_bin, cdiv(s->nC, 128), 128, 0, c.qc, cpos, s->d_crad.p, s->nC,
+                                         c.prm, s->d_circ_tile_count.p, s->d_circ_tile_ids.p, s->d_circ_snap.p));
         if (c.branch && c.qc != c.st) {
             CK(cudaEventRecord(s->ev_join[0], c.qc));
             c.circ_joined = true;
@@ -888,8 +888,8 @@ int Ops::launch_circle_chain(SubstepCtx &c) {
     }
     if (s->nC >= 2) {
         const size_t smem = s->nC <= 4096 ? (size_t)s->nC * 12 : 0;
-        LAUNCH(BENDY_K_CIRCLE_PASS,
-               k_circles_exact<<<1, 1024, smem, c.qc>>>(cpos, s->d_crad.p, s->nC, smem ? 1 : 0, s->d_flags.p + 1));
+        LAUNCH(BENDY_K_CIRCLE_PASS, launch_k(c.pdl > 2, k_circles_exact, 1, 1024, smem, c.qc, cpos, s->d_crad.p, s->nC,
+                                             smem ? 1 : 0, s->d_flags.p + 1));
     }
     return BENDY_OK;
 }
@@ -1004,9 +1004,8 @@ int Ops::launch_collide_integrate_discs(const SubstepCtx &c) {
         if (c.qc != st) CK(cudaStreamWaitEvent(c.qc, s->ev_main, 0));
         const uint32_t blocks_c = cdiv(s->nC, 128);
 #define CTAIL(A, KK)                                                                                            \
-    LAUNCH(BENDY_K_CIRCLES, k_circle_tail<A, KK, true><<<blocks_c, 128, 0, c.qc>>>(c.k1, s->d_circ_acc.p,       \
-                                                                                   s->d_circ_tile_count.p,     \
-                                                                                   s->n_circ_tiles, c.prm))
+    LAUNCH(BENDY_K_CIRCLES, launch_k(c.pdl > 2, k_circle_tail<A, KK, true>, blocks_c, 128, 0, c.qc, c.k1,           \
+                                     s->d_circ_acc.p, s->d_circ_tile_count.p, s->n_circ_tiles, c.prm))
         if (c.acc && c.K)
             CTAIL(true, true);
         else if (c.acc)
@@ -1021,13 +1020,13 @@ int Ops::launch_collide_integrate_discs(const SubstepCtx &c) {
         if (c.qg != st) CK(cudaStreamWaitEvent(c.qg, s->ev_main, 0));
         const uint32_t first = s->nP + s->nC, n = s->nG, blocks_g = cdiv(n, 256);
         if (c.acc && c.K)
-            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, true><<<blocks_g, 256, 0, c.qg>>>(c.k1, first, n, c.prm));
+            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<true, true>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
         else if (c.acc)
-            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<true, false><<<blocks_g, 256, 0, c.qg>>>(c.k1, first, n, c.prm));
+            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<true, false>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
         else if (c.K)
-            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, true><<<blocks_g, 256, 0, c.qg>>>(c.k1, first, n, c.prm));
+            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<false, true>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
         else
-            LAUNCH(BENDY_K_INTEGRATE, k1_integrate_range<false, false><<<blocks_g, 256, 0, c.qg>>>(c.k1, first, n, c.prm));
+            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<false, false>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
     }
     return BENDY_OK;
 }
