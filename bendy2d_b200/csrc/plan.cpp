@@ -154,8 +154,11 @@ bool plan_links(size_t n_points, const uint32_t *ab, const float *len, size_t n_
         uint32_t a = P.rank[ab[2 * k]], b = P.rank[ab[2 * k + 1]];
         if (part_of[a] == part_of[b]) {
             int c = lowest_free(lmask[a], lmask[b]);
-            if (c < 0) {
-                if (err) *err = "link planner: a point has more than 128 links (colour mask overflow)";
+            if (c < 0 || c >= (int)kMaxLocalColours) {
+                // greedy edge colouring needs at most 2*degree-1 colours: degree <= 128 always fits
+                if (err)
+                    *err = "link planner: more than 255 link colours needed inside one partition (a point with more "
+                           "than 128 links can cause this)";
                 return false;
             }
             mark(lmask[a], c), mark(lmask[b], c);
@@ -165,7 +168,7 @@ bool plan_links(size_t n_points, const uint32_t *ab, const float *len, size_t n_
             if (gmask.empty()) gmask.resize(n_linked);
             int c = lowest_free(gmask[a], gmask[b]);
             if (c < 0) {
-                if (err) *err = "link planner: a point has more than 128 cross-partition links";
+                if (err) *err = "link planner: more than 256 colours needed for the cross-partition links";
                 return false;
             }
             mark(gmask[a], c), mark(gmask[b], c);

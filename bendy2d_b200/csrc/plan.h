@@ -27,6 +27,9 @@ struct GlobalLink {  // 12 B record of a cross-partition link (internal point in
     float len;
 };
 
+// the partition kernel keeps the colour offsets of its partition in a 256-entry shared-memory table
+constexpr uint32_t kMaxLocalColours = 255;
+
 struct PlanParams {
     uint32_t pack_points = 512;  // keep adding whole components to a partition up to this many points
     uint32_t max_points = 4096;  // hard cap (shared memory: 8 B per point)
