@@ -469,6 +469,28 @@ int Ops::rebuild() {
     if (!plan_links(s->nOwned, s->pl_ab.data(), s->pl_len.data(), s->pl_len.size(), s->plan_params, false, &s->plan_p,
                     &perr, prio.empty() ? nullptr : prio.data()))
         return fail(BENDY_ERR_UNSUPPORTED, perr);
+    // ---- shared-memory opt-in: a CTA may use up to 227 KB, but anything above 48 KB (static + dynamic)
+    // has to be requested per kernel
+    {
+        uint32_t maxp = 0;
+        for (uint32_t p = 0; p < s->plan_p.n_parts(); p++)
+            maxp = std::max(maxp, s->plan_p.part_start[p + 1] - s->plan_p.part_start[p]);
+        const bool with_k = !s->p_k.empty() || !s->c_k.empty();
+        const size_t k3_bytes = (size_t)maxp * (with_k ? 12 : 8);
+        if (k3_bytes > 40 * 1024) {
+            const int b = (int)k3_bytes;
+            const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+            CK(cudaFuncSetAttribute(k3_links_local<false, false, 0>, at, b));
+            CK(cudaFuncSetAttribute(k3_links_local<false, true, 0>, at, b));
+            CK(cudaFuncSetAttribute(k3_links_local<true, false, 0>, at, b));
+            CK(cudaFuncSetAttribute(k3_links_local<true, true, 0>, at, b));
+            CK(cudaFuncSetAttribute(k3_links_local<false, true, 1>, at, b));
+            CK(cudaFuncSetAttribute(k3_links_local<false, true, 2>, at, b));
+        }
+        // k_circles_exact: 45 KB of static tables + 12 B per circle (up to 4096 circles) of dynamic
+        if (s->nC > 128 && s->nC <= 4096)
+            CK(cudaFuncSetAttribute(k_circles_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 12));
+    }
     // ---- state upload (internal order)
     std::vector<float2> pos(s->Npad), prev(s->Npad);
     for (uint32_t i = 0; i < s->nOwned; i++) {
@@ -1815,6 +1837,11 @@ int bendy_set_circle_inv_mass(bendy_solver *s, size_t first, size_t n, const flo
 }
 int bendy_set_plan_params(bendy_solver *s, uint32_t pack_points, uint32_t max_points) {
     NEED(s);
+    OPS;
+    // a partition lives in one CTA's shared memory (12 B per point with inverse masses, 227 KB per CTA)
+    // and its link records address points with 16 bits
+    if (max_points == 1 || max_points > 16384 || pack_points > 16384)
+        return ops.fail(BENDY_ERR_ARG, "bendy_set_plan_params: pack_points <= 16384 and 2 <= max_points <= 16384");
     if (pack_points) s->plan_params.pack_points = pack_points;
     if (max_points) s->plan_params.max_points = max_points;
     s->topo_dirty = true;
@@ -2100,6 +2127,10 @@ int bendy_plan_links(size_t n_points, const uint32_t *ab, size_t n_links, uint32
             g_last_error = "bendy_plan_links: link needs a < b < n_points";
             return BENDY_ERR_LINK;
         }
+    if (max_points == 1 || max_points > 16384 || pack_points > 16384) {
+        g_last_error = "bendy_plan_links: pack_points <= 16384 and 2 <= max_points <= 16384";
+        return BENDY_ERR_ARG;
+    }
     PlanParams pp;
     if (pack_points) pp.pack_points = pack_points;
     if (max_points) pp.max_points = max_points;

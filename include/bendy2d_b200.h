@@ -122,7 +122,8 @@ int bendy_set_polygon_contact(bendy_solver *s, int on);
 /* ext: inverse-mass scale per particle / circle; default 1 (= reference arithmetic); 0 pins the point */
 int bendy_set_particle_inv_mass(bendy_solver *s, size_t first, size_t n, const float *k);
 int bendy_set_circle_inv_mass(bendy_solver *s, size_t first, size_t n, const float *k);
-/* planner knobs: points per shared-memory partition (pack target, hard cap); 0 keeps the default */
+/* planner knobs: points per shared-memory partition (pack target, hard cap); 0 keeps the default (512, 4096).
+ * Limits: pack_points <= 16384, 2 <= max_points <= 16384 (one partition = one CTA's shared memory). */
 int bendy_set_plan_params(bendy_solver *s, uint32_t pack_points, uint32_t max_points);
 
 /* ---------------------------------------------------------------- schedule export (parity replay) */
