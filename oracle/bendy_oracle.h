@@ -10,7 +10,10 @@
  * PARITY PIN STATUS: the reference ships no tests, fixtures or golden vectors and cannot be
  * compiled here (no Rust toolchain, nalgebra 0.32.x not vendored).  The oracle is pinned by
  * (i) the cited source lines, (ii) hand-derived known-answer tests (tests/test_oracle_kat.py,
- * SURVEY.md §4).  Every function that has NO reference counterpart (the "ext" functions:
+ * SURVEY.md §4), (iii) a second restatement in numpy float32 written separately from the Rust
+ * lines (tests/np_restatement.py), compared bit for bit on random inputs and whole updates
+ * (tests/test_oracle_vs_numpy.py).  None of these is the reference itself: PARITY UNPINNED.
+ * Every function that has NO reference counterpart (the "ext" functions:
  * disc Jacobi contact, particle-vs-polygon closest-edge contact, inv_mass) is
  * "parity unpinned by the reference" and says so at its definition.
  *
