@@ -162,6 +162,14 @@ impl Solver {
     pub fn set_sub_steps(&mut self, n: u16) { self.ck(unsafe { sys::bendy_set_sub_steps(self.handle, n) }); }
     pub fn set_particle_radius(&mut self, r: f32) { self.ck(unsafe { sys::bendy_set_particle_radius(self.handle, r) }); }
     pub fn set_polygon_contact(&mut self, on: bool) { self.ck(unsafe { sys::bendy_set_polygon_contact(self.handle, on as i32) }); }
+
+    /// The state `clone()` copies, as one flat file (format: bendy2d_b200/snapshot.py).  Loading goes through
+    /// `bendy2d_sys::bendy_load_snapshot`; rebuilding this façade's AoS mirrors from a loaded handle is not
+    /// written yet.
+    pub fn save_snapshot(&mut self, path: &std::path::Path) {
+        let c = std::ffi::CString::new(path.to_string_lossy().as_bytes()).expect("path contains a NUL byte");
+        self.ck(unsafe { sys::bendy_save_snapshot(self.handle, c.as_ptr()) });
+    }
 }
 
 impl Clone for Solver {
