@@ -39,3 +39,28 @@ def test_algorithmic_bytes_match_survey_formula():
     expect = n_pts * 32 + n_disc * 56 + cells * 16 + n_link * 44 + (
         sc.n_particles * 16 + sc.n_polygon_points * 8 + len(sc.polygons) * 24)
     assert b["total"] == expect
+
+
+def test_committed_bench_line_follows_the_contract():
+    """profiles/r1_bench_c3_n1.json is the JSON line of `python bench.py` on a B200: every key of the bench
+    contract is there and the derived figures are consistent with each other."""
+    with open(os.path.join(ROOT, "profiles", "r1_bench_c3_n1.json")) as f:
+        d = json.loads(f.read().strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["metric"] == "particle-substeps/s" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["dtype"] == "f32"
+    assert "workload" in d["config"] and "C3" in d["config"]["workload"] and "flush" in d["config"]["l2"]
+    sub = d["config"]["substeps_per_step"]
+    assert abs(d["value"] - d["config"]["points"] * sub / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(r["achieved"] - r["alg_bytes_per_substep_kernel"] / (r["avg_launch_ms"] * 1e-3) / 1e9) / r["achieved"] < 1e-6
+    whole = r["substep"]
+    assert abs(whole["achieved"] - whole["alg_bytes"] * sub / (d["ms_per_step"] * 1e-3) / 1e9) / whole["achieved"] < 1e-6
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+    assert d["gpu_launches"] == d["steps"] * sub * d["schedule"]["kernels_per_substep"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] == 1 and c["value"] > 0 and "sample" in c
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
