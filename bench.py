@@ -416,7 +416,14 @@ def main():
                    "circles": len(sc.circles_r), "polygons": len(sc.polygons), "substeps_per_step": sc.sub_steps,
                    "substep_dt": 1.0 / 120.0 if workload != "c1" else 1.0 / 480.0,
                    "l2": "warm between steps" if args.no_flush else "flushed between steps (256 MiB memset)",
-                   "parallelism": f"strips{world}" if world > 1 else "single"},
+                   "parallelism": f"strips{world}" if world > 1 else "single",
+                   # the N=1 line's headline is C3 (the 1-GPU configuration); N>1 lines shard C5.  The N=1
+                   # point of the C5 strong-scaling series is `strong_scaling_reference_c5_n1` of the N=1 line.
+                   "series_note": ("C5 sharded over strips, total work fixed; compare with "
+                                   "strong_scaling_reference_c5_n1 of the N=1 line, not with its C3 headline")
+                   if world > 1 else
+                   ("headline = C3 on one GPU; strong_scaling_reference_c5_n1 is the N=1 point of the C5 series "
+                    "that --gpus 2/4/8 continue")},
         "value_warm_l2": value_warm, "wall_s_timed_region": wall,
         "ms_per_step_series": [round(x, 4) for x in step_ms],
         "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
