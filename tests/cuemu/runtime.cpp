@@ -1,0 +1,450 @@
+// runtime.cpp (cuemu) — TEST INFRASTRUCTURE: fiber scheduler + the host-side CUDA runtime calls that
+// bendy2d_b200/csrc/solver.cu makes.  See include/cuda_runtime.h for the model and its limits.
+#include <cuda_runtime.h>
+#include <sys/mman.h>
+
+#include <chrono>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+uint3 threadIdx, blockIdx;
+dim3 blockDim, gridDim;
+
+namespace cuemu {
+
+Globals g;
+
+// ------------------------------------------------------------------------------------------------
+// context switch (x86-64 SysV): callee-saved registers + stack pointer
+extern "C" void cuemu_switch(void **save_sp, void *new_sp);
+asm(R"(
+.text
+.globl cuemu_switch
+.type cuemu_switch,@function
+cuemu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size cuemu_switch,.-cuemu_switch
+)");
+
+struct Cta {
+    uint3 bid;
+    uint32_t live = 0, at_barrier = 0;
+    std::vector<WarpState> warps;
+    std::vector<Fiber *> fibers;
+    std::vector<unsigned char> dyn;
+    std::unordered_map<int, std::unique_ptr<unsigned char[]>> stat;
+};
+
+struct Graph {
+    std::vector<std::function<void()>> ops;
+};
+struct GraphExec {
+    std::vector<std::function<void()>> ops;
+};
+struct Stream {
+    int id;
+};
+struct Event {
+    std::chrono::steady_clock::time_point t;
+};
+
+namespace {
+
+constexpr size_t kStack = 256 * 1024;
+constexpr uint32_t kPool = 2048;  // fibers = the most CUDA threads resident at once (8 "SMs" x 256)
+constexpr int kMaxDynDefault = 48 * 1024, kMaxDynOptIn = 227 * 1024;
+
+std::recursive_mutex g_mu;  // one launch at a time, whichever OS thread it comes from
+void *g_sched_sp = nullptr;
+std::vector<Fiber *> g_pool;
+const std::function<void()> *g_body = nullptr;
+const char *g_kernel_name = "?";
+cudaError_t g_last = cudaSuccess;
+Graph *g_capture = nullptr;
+std::unordered_map<const void *, int> g_max_dyn;
+struct Alloc {
+    size_t bytes;
+};
+std::map<void *, Alloc> g_allocs;
+constexpr size_t kGuard = 256;
+constexpr unsigned char kCanary = 0xA5, kPoisonDev = 0xEE, kPoisonSmem = 0xCD;
+
+[[noreturn]] void die(const char *what) {
+    fprintf(stderr, "[cuemu] FATAL in kernel %s: %s\n", g_kernel_name, what);
+    fflush(stderr);
+    abort();
+}
+
+void to_scheduler() {
+    Fiber *f = g.cur;
+    cuemu_switch(&f->sp, g_sched_sp);
+}
+
+void release_barrier(Cta *c) {
+    for (Fiber *f : c->fibers) f->at_barrier = false;
+    c->at_barrier = 0;
+    g.events++;
+}
+
+void fiber_entry() {
+    for (;;) {
+        Fiber *f = g.cur;
+        (*g_body)();
+        // thread exit: it no longer takes part in barriers or warp exchanges
+        f = g.cur;
+        f->done = true;
+        Cta *c = f->cta;
+        c->warps[f->warp].live &= ~(1u << f->lane);
+        c->live--;
+        g.events++;
+        if (c->live > 0 && c->at_barrier == c->live) release_barrier(c);
+        to_scheduler();
+    }
+}
+
+Fiber *make_fiber() {
+    Fiber *f = new Fiber();
+    void *m = mmap(nullptr, kStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (m == MAP_FAILED) die("mmap of a fiber stack failed");
+    mprotect(m, 4096, PROT_NONE);  // guard page at the low end
+    f->stack = m;
+    uintptr_t top = ((uintptr_t)m + kStack) & ~(uintptr_t)15;
+    void **sp = (void **)top;
+    *--sp = nullptr;                 // fake return address of fiber_entry (never used)
+    *--sp = (void *)&fiber_entry;    // `ret` of the first switch jumps here
+    for (int k = 0; k < 6; k++) *--sp = nullptr;  // rbp rbx r12 r13 r14 r15
+    f->sp = sp;
+    return f;
+}
+
+void resume(Fiber *f) {
+    g.cur = f;
+    threadIdx = f->tid;
+    blockIdx = f->cta->bid;
+    cuemu_switch(&g_sched_sp, f->sp);
+}
+
+void run_batch(std::vector<Cta> &ctas, uint32_t threads, size_t smem) {
+    uint32_t remaining = 0, next = 0;
+    for (Cta &c : ctas) {
+        c.live = threads;
+        c.at_barrier = 0;
+        c.warps.assign((threads + 31) / 32, WarpState{});
+        c.dyn.assign(smem, kPoisonSmem);
+        c.stat.clear();
+        c.fibers.clear();
+        for (uint32_t t = 0; t < threads; t++) {
+            if (next >= g_pool.size()) g_pool.push_back(make_fiber());
+            Fiber *f = g_pool[next++];
+            f->tid = uint3{t, 0, 0};
+            f->lane = t & 31, f->warp = t >> 5;
+            f->cta = &c;
+            f->done = false, f->at_barrier = false;
+            f->warp_op = 0;
+            c.warps[f->warp].live |= 1u << f->lane;
+            c.fibers.push_back(f);
+            remaining++;
+        }
+    }
+    while (true) {
+        const uint64_t ev0 = g.events;
+        uint32_t alive = 0;
+        for (Cta &c : ctas)
+            for (Fiber *f : c.fibers) {
+                if (f->done) continue;
+                alive++;
+                if (f->at_barrier) continue;
+                resume(f);
+            }
+        if (!alive) break;
+        if (g.events == ev0) die("deadlock: no thread made progress (mismatched barrier / warp primitive, or a grid barrier whose CTAs are not all resident)");
+    }
+    (void)remaining;
+}
+
+void run_kernel(const char *name, dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (g_body) die("nested kernel launch");
+    g_kernel_name = name;
+    const uint32_t threads = block.x;
+    const uint32_t per_batch = std::max(1u, kPool / threads);
+    gridDim = grid, blockDim = block;
+    g_body = &body;
+    for (uint32_t b0 = 0; b0 < grid.x; b0 += per_batch) {
+        const uint32_t nb = std::min(per_batch, grid.x - b0);
+        std::vector<Cta> ctas(nb);
+        for (uint32_t k = 0; k < nb; k++) ctas[k].bid = uint3{b0 + k, 0, 0};
+        run_batch(ctas, threads, smem);
+    }
+    g_body = nullptr;
+    g.cur = nullptr;
+}
+
+void check_canaries(const char *when) {
+    for (auto &kv : g_allocs) {
+        const unsigned char *base = (const unsigned char *)kv.first;
+        for (size_t k = 0; k < kGuard; k++)
+            if (base[-(ptrdiff_t)kGuard + (ptrdiff_t)k] != kCanary || base[kv.second.bytes + k] != kCanary) {
+                fprintf(stderr, "[cuemu] FATAL: out-of-bounds write next to device allocation %p (%zu bytes), found %s; last kernel %s\n",
+                        kv.first, kv.second.bytes, when, g_kernel_name);
+                abort();
+            }
+    }
+}
+
+template <typename F>
+cudaError_t enqueue(F &&f) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (g_capture)
+        g_capture->ops.emplace_back(std::forward<F>(f));
+    else
+        f();
+    return cudaSuccess;
+}
+
+}  // namespace
+
+void *dyn_smem() { return g.cur->cta->dyn.data(); }
+
+void *static_smem(int id, size_t bytes) {
+    auto &m = g.cur->cta->stat;
+    auto it = m.find(id);
+    if (it == m.end()) {
+        std::unique_ptr<unsigned char[]> p(new unsigned char[bytes + 16]);
+        memset(p.get(), kPoisonSmem, bytes + 16);
+        it = m.emplace(id, std::move(p)).first;
+    }
+    // 16-byte alignment is what new[] gives on x86-64
+    return it->second.get();
+}
+
+void sync_block() {
+    Fiber *f = g.cur;
+    Cta *c = f->cta;
+    f->at_barrier = true;
+    c->at_barrier++;
+    g.events++;
+    if (c->at_barrier == c->live) {
+        release_barrier(c);
+        return;
+    }
+    while (f->at_barrier) to_scheduler();
+}
+
+void yield_spin() { to_scheduler(); }
+
+uint32_t warp_live() { return g.cur->cta->warps[g.cur->warp].live; }
+
+WarpSlot &warp_arrive(uint32_t mask, uint64_t v, uint32_t *participants) {
+    Fiber *f = g.cur;
+    WarpState &w = f->cta->warps[f->warp];
+    WarpSlot &s = w.slot[f->warp_op++ & 1u];
+    const uint32_t bit = 1u << f->lane;
+    if (!(mask & bit)) die("a lane called a *_sync primitive with a mask that excludes itself");
+    if (s.arrive & bit) die("warp primitive slot reused before every participant read it (divergent *_sync calls)");
+    s.vals[f->lane] = v;
+    s.arrive |= bit;
+    g.events++;
+    while (true) {
+        const uint32_t need = mask & w.live;
+        if ((s.arrive & need) == need) break;
+        to_scheduler();
+    }
+    *participants = s.arrive & mask;
+    return s;
+}
+
+void warp_done(WarpSlot &s, uint32_t participants) {
+    Fiber *f = g.cur;
+    s.read |= 1u << f->lane;
+    if ((s.read & participants) == participants) s.arrive = 0, s.read = 0;
+}
+
+void set_max_dyn_smem(const void *fn_key, int bytes) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (bytes > kMaxDynOptIn)
+        g_last = cudaErrorInvalidValue;
+    else
+        g_max_dyn[fn_key] = bytes;
+}
+
+void launch(const char *name, const void *fn_key, dim3 grid, dim3 block, size_t smem, cudaStream_t, std::function<void()> body) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (grid.x == 0 || block.x == 0 || block.x > 1024 || grid.y != 1 || grid.z != 1 || block.y != 1 || block.z != 1) {
+        g_last = cudaErrorInvalidConfiguration;
+        return;
+    }
+    auto it = g_max_dyn.find(fn_key);
+    const int allowed = it == g_max_dyn.end() ? kMaxDynDefault : std::max(it->second, kMaxDynDefault);
+    if (smem > (size_t)allowed) {  // what a real launch answers when the opt-in is missing
+        g_last = cudaErrorInvalidValue;
+        return;
+    }
+    std::string nm(name);
+    enqueue([nm, grid, block, smem, body]() { run_kernel(nm.c_str(), grid, block, smem, body); });
+}
+
+}  // namespace cuemu
+
+using namespace cuemu;
+
+// ------------------------------------------------------------------------------------------------
+const char *cudaGetErrorName(cudaError_t e) {
+    switch (e) {
+        case cudaSuccess: return "cudaSuccess";
+        case cudaErrorInvalidValue: return "cudaErrorInvalidValue";
+        case cudaErrorMemoryAllocation: return "cudaErrorMemoryAllocation";
+        case cudaErrorInvalidConfiguration: return "cudaErrorInvalidConfiguration";
+        default: return "cudaErrorLaunchFailure";
+    }
+}
+const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "cuemu: emulated CUDA error"; }
+cudaError_t cudaGetLastError() {
+    cudaError_t e = g_last;
+    g_last = cudaSuccess;
+    return e;
+}
+cudaError_t cudaPeekAtLastError() { return g_last; }
+cudaError_t cudaGetDeviceCount(int *n) {
+    *n = 1;
+    return cudaSuccess;
+}
+cudaError_t cudaGetDevice(int *d) {
+    *d = 0;
+    return cudaSuccess;
+}
+cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) {
+    *v = 8;  // "SMs": 8 x 256 threads = the fiber pool
+    return cudaSuccess;
+}
+cudaError_t cudaDeviceGetStreamPriorityRange(int *least, int *greatest) {
+    *least = 0, *greatest = -1;
+    return cudaSuccess;
+}
+
+cudaError_t cuemuMalloc(void **p, size_t bytes) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const size_t padded = (bytes + 255) & ~(size_t)255;
+    unsigned char *raw = (unsigned char *)aligned_alloc(256, padded + 2 * kGuard);
+    if (!raw) return cudaErrorMemoryAllocation;
+    memset(raw, kCanary, kGuard);
+    memset(raw + kGuard, kPoisonDev, bytes);            // cudaMalloc memory is NOT zeroed
+    memset(raw + kGuard + bytes, kCanary, padded - bytes + kGuard);
+    *p = raw + kGuard;
+    g_allocs[*p] = Alloc{bytes};
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void *p) {
+    if (!p) return cudaSuccess;
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    check_canaries("at cudaFree");
+    g_allocs.erase(p);
+    free((unsigned char *)p - kGuard);
+    return cudaSuccess;
+}
+cudaError_t cuemuHostAlloc(void **p, size_t bytes) {
+    *p = aligned_alloc(256, (bytes + 255) & ~(size_t)255);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFreeHost(void *p) {
+    free(p);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (g_capture) return cudaErrorInvalidValue;  // a synchronous copy during stream capture is an error
+    memcpy(dst, src, n);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) {
+    return enqueue([dst, src, n]() { memmove(dst, src, n); });
+}
+cudaError_t cudaMemsetAsync(void *dst, int v, size_t n, cudaStream_t) {
+    return enqueue([dst, v, n]() { memset(dst, v, n); });
+}
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
+    static int ids = 0;
+    *s = new Stream{++ids};
+    return cudaSuccess;
+}
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned flags, int) { return cudaStreamCreateWithFlags(s, flags); }
+cudaError_t cudaStreamDestroy(cudaStream_t s) {
+    delete s;
+    return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (g_capture) return cudaErrorInvalidValue;
+    check_canaries("at cudaStreamSynchronize");
+    return cudaSuccess;
+}
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }  // issue order already respects it
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (g_capture) return cudaErrorInvalidValue;
+    g_capture = new Graph();
+    return cudaSuccess;
+}
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!g_capture) return cudaErrorInvalidValue;
+    *out = g_capture;
+    g_capture = nullptr;
+    return cudaSuccess;
+}
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t *e, cudaGraph_t gr, unsigned long long) {
+    *e = new GraphExec{gr->ops};
+    return cudaSuccess;
+}
+cudaError_t cudaGraphDestroy(cudaGraph_t gr) {
+    delete gr;
+    return cudaSuccess;
+}
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) {
+    delete e;
+    return cudaSuccess;
+}
+cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (g_capture) return cudaErrorInvalidValue;
+    for (auto &op : e->ops) op();
+    return cudaSuccess;
+}
+cudaError_t cudaEventCreate(cudaEvent_t *e) {
+    *e = new Event{std::chrono::steady_clock::now()};
+    return cudaSuccess;
+}
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) {
+    delete e;
+    return cudaSuccess;
+}
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
+    e->t = std::chrono::steady_clock::now();
+    return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return cudaSuccess;
+}
