@@ -166,6 +166,9 @@ struct bendy_solver {
     DevBuf<uint32_t> d_cell_count, d_cell_start, d_tile_sum, d_sorted_id, d_slot_of;
     DevBuf<uint32_t> d_scan_barrier;
     uint32_t scan_fused_capacity = 0;  // CTAs of k2_scan_fused that can be resident at once
+    bool scan_mt = false;              // BENDY_SCAN_MT=1: k2_scan_fused_mt<2|4> when one tile per CTA does not fit
+    uint32_t scan_mt_capacity[2] = {0, 0};  // resident CTAs of k2_scan_fused_mt<2>, <4>
+    uint32_t scan_tiles_per_cta = 1;
     uint32_t k3_threads = 128;  // BENDY_K3_THREADS
     bool scatter_agg = false;   // BENDY_SCATTER_AGG
     bool halo_overlap = false;  // BENDY_HALO_OVERLAP
@@ -701,6 +704,29 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
                 if (const char *v = getenv("BENDY_SCAN_FUSED"))
                     if (atoi(v) == 0) s->scan_fused_capacity = 1;
             }
+            // opt-in: several tiles per CTA so that a larger histogram still scans in one resident wave
+            s->scan_tiles_per_cta = 1;
+            if (s->scan_mt && (uint64_t)s->n_scan_tiles * 100 > (uint64_t)s->scan_fused_capacity * 85) {
+                if (!s->scan_mt_capacity[0]) {
+                    int per_sm = 0, sms = 0;
+                    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_fused_mt<2>, SCAN_THREADS, 0));
+                    s->scan_mt_capacity[0] = (uint32_t)std::max(per_sm * sms, 1);
+                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_fused_mt<4>, SCAN_THREADS, 0));
+                    s->scan_mt_capacity[1] = (uint32_t)std::max(per_sm * sms, 1);
+                }
+                for (uint32_t k = 0; k < 2 && s->scan_tiles_per_cta == 1; k++) {
+                    const uint32_t T = 2u << k;
+                    if ((uint64_t)cdiv(s->n_scan_tiles, T) * 100 <= (uint64_t)s->scan_mt_capacity[k] * 85) s->scan_tiles_per_cta = T;
+                }
+                if (s->scan_tiles_per_cta > 1) {  // whole CTAs: the extra tiles are empty cells behind the grid
+                    s->n_scan_tiles = cdiv(s->n_scan_tiles, s->scan_tiles_per_cta) * s->scan_tiles_per_cta;
+                    padded = (size_t)s->n_scan_tiles * SCAN_TILE;
+                    CK(s->d_cell_count.ensure(padded));
+                    CK(cudaMemsetAsync(s->d_cell_count.p, 0, padded * sizeof(uint32_t), s->stream));
+                    CK(s->d_cell_start.ensure(padded));
+                }
+            }
             CK(s->d_tile_sum.ensure(s->n_scan_tiles));
             CK(cudaMemsetAsync(s->d_tile_sum.p, 0, (size_t)s->n_scan_tiles * sizeof(uint32_t), s->stream));
             if (s->nC) {
@@ -975,7 +1001,13 @@ int Ops::launch_particle_links(const SubstepCtx &c, int phase, bool *ghosts_done
 int Ops::launch_grid_build(const SubstepCtx &c) {
     if (!c.discs) return BENDY_OK;
     cudaStream_t st = c.st;
-    if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->scan_fused_capacity * 85) {
+    if (s->scan_tiles_per_cta == 2) {
+        LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan_fused_mt<2>, s->n_scan_tiles / 2, SCAN_THREADS, 0, st,
+                                            s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
+    } else if (s->scan_tiles_per_cta == 4) {
+        LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan_fused_mt<4>, s->n_scan_tiles / 4, SCAN_THREADS, 0, st,
+                                            s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
+    } else if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->scan_fused_capacity * 85) {
         // every scan CTA fits on the device at once (15% spare; side-branch kernels finish on their own)
         LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan_fused, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
                                             s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
@@ -1270,6 +1302,7 @@ bendy_solver *bendy_create(int device) {
     if (const char *v = getenv("BENDY_SCATTER_AGG")) s->scatter_agg = atoi(v) != 0;
     if (const char *v = getenv("BENDY_HALO_OVERLAP")) s->halo_overlap = atoi(v) != 0;
     if (const char *v = getenv("BENDY_SMALL_SCENE")) s->small_scene = atoi(v) != 0;
+    if (const char *v = getenv("BENDY_SCAN_MT")) s->scan_mt = atoi(v) != 0;
     if (const char *v = getenv("BENDY_PDL")) s->pdl = atoi(v);
     if (const char *v = getenv("BENDY_PDL_NCCL")) s->pdl_nccl = atoi(v) != 0;
     // BENDY_SIDE_PRIORITY=1: the circle / polygon branches get the highest stream priority, so their few
@@ -1931,6 +1964,7 @@ int bendy_get_stats(bendy_solver *s, uint64_t *out, int n) {
     OPS;
     if (!out || n < 1) return ops.fail(BENDY_ERR_ARG, "bendy_get_stats: bad arguments");
     for (int k = 0; k < n; k++) out[k] = 0;
+    if (n > 4) out[4] = s->scan_tiles_per_cta;  // 2 / 4: k2_scan_fused_mt is in use (BENDY_SCAN_MT)
     if (!s->d_flags.p) return BENDY_OK;
     if (int rc = ops.bind()) return rc;
     int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};

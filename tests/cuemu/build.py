@@ -69,8 +69,8 @@ def transform(text: str, name: str) -> str:
         left = [ln for ln in text.splitlines() if "__shared__" in ln and not ln.lstrip().startswith("//")]
         if left:
             raise SystemExit(f"cuemu/build.py: unconverted __shared__ in {name}: {left[0].strip()}")
-    if name == "kernels.cuh" and n_spin != 1:
-        raise SystemExit("cuemu/build.py: the grid-barrier spin loop of k2_scan_fused was not found (kernel changed?)")
+    if name == "kernels.cuh" and n_spin < 1:
+        raise SystemExit("cuemu/build.py: no grid-barrier spin loop (k2_scan_fused*) was found (kernel changed?)")
     return text
 
 
