@@ -166,6 +166,8 @@ struct bendy_solver {
     DevBuf<uint32_t> d_cell_count, d_cell_start, d_tile_sum, d_sorted_id, d_slot_of;
     DevBuf<uint32_t> d_scan_barrier;
     uint32_t scan_fused_capacity = 0;  // CTAs of k2_scan_fused that can be resident at once
+    bool halo_fused = false;           // BENDY_HALO_FUSED=1: send-buffer reset + ghost histogram in one launch
+    bool narrow_dense = false;         // BENDY_NARROW_DENSE=1: k2_narrow_dense (lane-dense contact resolution)
     bool scan_mt = false;              // BENDY_SCAN_MT=1: k2_scan_fused_mt<2|4> when one tile per CTA does not fit
     uint32_t scan_mt_capacity[2] = {0, 0};  // resident CTAs of k2_scan_fused_mt<2>, <4>
     uint32_t scan_tiles_per_cta = 1;
@@ -957,6 +959,12 @@ int Ops::launch_count_unlinked(const SubstepCtx &c) {
 
 // strips: my send buffers were consumed -> reset them; the received ghosts join the histogram
 int Ops::launch_halo_receive(const SubstepCtx &c, cudaStream_t q_clear) {
+    if (s->halo_fused && q_clear == c.st) {
+        const uint32_t n = std::max(s->ghost_cap, s->nP - s->nOwned);
+        LAUNCH(BENDY_K_HALO, launch_k(c.pdl > 0, k_halo_receive, cdiv(n, 256), 256, 0, c.st, s->d_send[0].p, s->d_send[1].p,
+                                      s->d_send_cnt.p, s->ghost_cap, c.pos, s->nOwned, s->nP, c.ca));
+        return BENDY_OK;
+    }
     LAUNCH(BENDY_K_HALO, k_halo_clear<<<cdiv(s->ghost_cap, 256), 256, 0, q_clear>>>(s->d_send[0].p, s->d_send[1].p,
                                                                                     s->d_send_cnt.p, s->ghost_cap));
     if (q_clear != c.st) {
@@ -1044,7 +1052,12 @@ int Ops::launch_collide_integrate_discs(const SubstepCtx &c) {
     const uint32_t blocks = cdiv(s->nOwned, 128);
 #define NARROW(HK, HP) \
     LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_contact_integrate<HK, HP>, blocks, 128, 0, st, a, c.k4, c.prm))
-    if (c.K && c.contact)
+    if (!c.K && s->narrow_dense) {
+        if (c.contact)
+            LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_dense<true>, blocks, 128, 0, st, a, c.k4, c.prm));
+        else
+            LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_dense<false>, blocks, 128, 0, st, a, c.k4, c.prm));
+    } else if (c.K && c.contact)
         NARROW(true, true);
     else if (c.K)
         NARROW(true, false);
@@ -1303,6 +1316,8 @@ bendy_solver *bendy_create(int device) {
     if (const char *v = getenv("BENDY_HALO_OVERLAP")) s->halo_overlap = atoi(v) != 0;
     if (const char *v = getenv("BENDY_SMALL_SCENE")) s->small_scene = atoi(v) != 0;
     if (const char *v = getenv("BENDY_SCAN_MT")) s->scan_mt = atoi(v) != 0;
+    if (const char *v = getenv("BENDY_NARROW_DENSE")) s->narrow_dense = atoi(v) != 0;
+    if (const char *v = getenv("BENDY_HALO_FUSED")) s->halo_fused = atoi(v) != 0;
     if (const char *v = getenv("BENDY_PDL")) s->pdl = atoi(v);
     if (const char *v = getenv("BENDY_PDL_NCCL")) s->pdl_nccl = atoi(v) != 0;
     // BENDY_SIDE_PRIORITY=1: the circle / polygon branches get the highest stream priority, so their few
@@ -1965,6 +1980,7 @@ int bendy_get_stats(bendy_solver *s, uint64_t *out, int n) {
     if (!out || n < 1) return ops.fail(BENDY_ERR_ARG, "bendy_get_stats: bad arguments");
     for (int k = 0; k < n; k++) out[k] = 0;
     if (n > 4) out[4] = s->scan_tiles_per_cta;  // 2 / 4: k2_scan_fused_mt is in use (BENDY_SCAN_MT)
+    if (n > 5) out[5] = (s->narrow_dense && !s->has_k) ? 1 : 0;
     if (!s->d_flags.p) return BENDY_OK;
     if (int rc = ops.bind()) return rc;
     int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};

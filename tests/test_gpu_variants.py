@@ -91,3 +91,87 @@ def test_multi_tile_fused_scan_matches_default_and_oracle(width, height, cell, t
         g.update(sc.dt)
         o.update(sc.dt)
     compare_state(g, o, max(width, height), 1e-5, "multi-tile scan")
+
+
+# ------------------------------------------------------------------------------------------------
+# BENDY_NARROW_DENSE=1: lane-dense resolution of the disc contacts (k2_narrow_dense)
+def test_dense_narrowphase_pile_matches_default_and_oracle():
+    sc = scenes.c2_free_particles(60, 40)
+    sc.bounds = (0.0, 0.0, 40.0, 16.0)  # shallow box: the pile forms within the test
+    n = 150
+    a = run(sc, n)
+    b = run(sc, n, BENDY_NARROW_DENSE=1)
+    assert b.stats()["narrow_dense"] == 1
+    same_bits(a, b)
+    g = run(sc, 0, BENDY_NARROW_DENSE=1)
+    o = oracle_from_scene(sc)
+    sync_schedule(g, o, sc)
+    for k in range(n):
+        g.update(sc.dt)
+        o.update(sc.dt)
+        if (k + 1) % 25 == 0:
+            compare_state(g, o, 40.0, 1e-5, f"dense narrowphase update {k + 1}")
+
+
+def test_dense_narrowphase_with_circles_polygons_and_links():
+    sc = scenes.c3_softbody_field(4, 2, 6, 8)
+    sc.bounds = (0.0, 0.0, 128.0, 64.0)
+    sc.particles = (sc.particles - np.array([40.0, 0.0], f32)).astype(f32)
+    a = run(sc, 120)
+    b = run(sc, 120, BENDY_NARROW_DENSE=1)
+    same_bits(a, b)
+    sc4 = scenes.c4_polygon_heavy(6, 150)
+    same_bits(run(sc4, 100), run(sc4, 100, BENDY_NARROW_DENSE=1))
+
+
+def test_dense_narrowphase_pool_flushes_when_a_warp_collects_more_pairs_than_it_holds():
+    # 40 x 24 discs squeezed into a patch 12 disc-diameters wide: every disc overlaps dozens of others, so
+    # a warp gathers far more than NARROW_POOL (192) pairs and has to resolve in several rounds; plus a
+    # non-finite disc and discs outside the bounds (clamped into the border cells)
+    rng = np.random.default_rng(7)
+    pts = (np.array([10.0, 10.0]) + rng.uniform(0.0, 2.4, size=(960, 2))).astype(f32)
+    pts[17] = [np.nan, 3.0]
+    pts[400] = [-5.0, 10.5]
+    pts[401] = [-5.05, 10.45]
+    sc = scenes.Scene("crowd", (0.0, 0.0, 32.0, 32.0), particle_radius=0.1, particles=pts)
+    for cell in (0.0, 0.2, 0.42):
+        same_bits(run(sc, 12, grid_cell=cell), run(sc, 12, grid_cell=cell, BENDY_NARROW_DENSE=1))
+
+
+def test_dense_narrowphase_on_strips_matches_single_solver():
+    from bendy2d_b200 import strips
+    from test_gpu_strips import touching_field
+
+    sc = touching_field()
+    ref = run(sc, 0)
+    ref.update(sc.dt, n=60)
+    with env(BENDY_NARROW_DENSE=1):
+        grp = strips.LocalStripGroup(sc, 3)
+    grp.update(sc.dt, n=60)
+    assert all(o == 0 and st == 0 for _, _, o, st in grp.halo_stats())
+    pos, prev = grp.read_particles()
+    rp, rq = ref.read_particles()
+    assert np.array_equal(bits(pos), bits(rp)) and np.array_equal(bits(prev), bits(rq))
+
+
+# ------------------------------------------------------------------------------------------------
+# BENDY_HALO_FUSED=1: send-buffer reset + ghost histogram in one launch; and everything switched on together
+@pytest.mark.parametrize("switches", [{"BENDY_HALO_FUSED": 1},
+                                      {"BENDY_HALO_FUSED": 1, "BENDY_NARROW_DENSE": 1, "BENDY_SCAN_MT": 1}])
+def test_strip_variants_match_single_solver(switches):
+    from bendy2d_b200 import strips
+    from test_gpu_strips import touching_field
+
+    sc = touching_field()
+    ref = run(sc, 0)
+    with env(**switches):
+        grp = strips.LocalStripGroup(sc, 4)
+    for k in range(3):
+        ref.update(sc.dt, n=20)
+        grp.update(sc.dt, n=20)
+        pos, prev = grp.read_particles()
+        rp, rq = ref.read_particles()
+        assert np.array_equal(bits(pos), bits(rp)) and np.array_equal(bits(prev), bits(rq)), f"after {20 * (k + 1)} substeps"
+    stats = grp.halo_stats()
+    assert all(o == 0 and st == 0 for _, _, o, st in stats), stats
+    assert sum(a + b for a, b, _, _ in stats) > 0
