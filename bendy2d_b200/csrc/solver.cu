@@ -371,7 +371,11 @@ int Ops::check_flags() {
     CK(cudaStreamSynchronize(s->stream));
     if (f) {
         CK(cudaMemsetAsync(s->d_flags.p, 0, sizeof(int), s->stream));
-        if (f & (FLAG_POLY_TILE_OVERFLOW | FLAG_POLY_SPAN_OVERFLOW))
+        // Only the particle-polygon contact (ext) takes its candidates from the tile lists.  The reference's
+        // polygon<->polygon pass is exact whatever the bins hold: the pair pre-scan answers an overflowing
+        // tile or an unbinned polygon with "start at row 0" and the pass itself compares all boxes.
+        const bool contact = s->polygon_contact && !s->polys.empty() && s->nOwned > 0;
+        if (contact && (f & (FLAG_POLY_TILE_OVERFLOW | FLAG_POLY_SPAN_OVERFLOW)))
             return fail(BENDY_ERR_UNSUPPORTED,
                         "polygon broadphase overflow: more than 7 polygons share one tile or a polygon spans "
                         "more than 64 tiles; particle-polygon contacts were dropped for the overflowing tiles");

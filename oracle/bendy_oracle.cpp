@@ -467,7 +467,13 @@ static void ext_disc_contacts(bo_world &w, const std::vector<V2> &QC) {
 // normal exactly as polygon.rs:175-181 does with the edge start as the on-line point; q is inside
 // iff every signed inward distance is > 0; the closest edge (smallest distance, lowest index on
 // ties) receives q via the reference's projection polygon.rs:206-209
-// (line_intersection(edge, (q, q - n_in*10000))).  Candidate polygons by ascending index.
+// (line_intersection(edge, (q, q - n_in*10000))).
+// Several obstacles (they may overlap): the CANDIDATES of a particle are the static polygons whose AABB
+// contains its position at the ENTRY of this step (after the disc contacts), taken in ascending polygon
+// index; each candidate is then tested (AABB again, inside test, projection) against the particle's
+// CURRENT position, i.e. after the projections of the earlier candidates.  A polygon the particle was not
+// inside the AABB of at entry is not revisited in this substep, even if a projection moves the particle
+// into it (it becomes a candidate in the next substep).  The rule is independent of any binning.
 static void ext_polygon_contacts(bo_world &w) {
     const size_t n = w.particles.size();
     struct Box {
@@ -510,11 +516,13 @@ static void ext_polygon_contacts(bo_world &w) {
     for (size_t i = 0; i < n; i++) {
         if (pk(w, i) == 0.0f) continue;
         V2 q = w.particles[i].pos;
+        const V2 q0 = q;  // position at entry: decides the candidate set
         if (!(q.x >= wx0 && q.x <= wx1 && q.y >= wy0 && q.y <= wy1)) continue;
         const std::vector<uint32_t> &cand = bins[(size_t)bcoord(q.y, wy0, by) * bx + bcoord(q.x, wx0, bx)];
         for (uint32_t k : cand) {  // ascending polygon index by construction
             const Box &b = boxes[k];
-            if (!(q.x >= b.x0 && q.x <= b.x1 && q.y >= b.y0 && q.y <= b.y1)) continue;
+            if (!(q0.x >= b.x0 && q0.x <= b.x1 && q0.y >= b.y0 && q0.y <= b.y1)) continue;  // not a candidate
+            if (!(q.x >= b.x0 && q.x <= b.x1 && q.y >= b.y0 && q.y <= b.y1)) continue;      // q may have moved
             const Polygon &P = w.polygons[k];
             const size_t E = P.particles.size();
             bool inside = true;

@@ -27,7 +27,7 @@ PY
   exit 0
 fi
 # 1. the variants' own parity tests on the device (default gpu run skips them until this has passed once)
-BENDY_TEST_UNPROVEN=1 timeout 600 python -m pytest tests/test_gpu_variants.py -m gpu -x -q > gpurun_out/r2_variant_tests.log 2>&1
+BENDY_TEST_UNPROVEN=1 timeout 600 python -m pytest tests/test_z_gpu_variants.py -m gpu -x -q > gpurun_out/r2_variant_tests.log 2>&1
 echo "variant tests exit code $?" | tee -a $OUT
 tail -3 gpurun_out/r2_variant_tests.log | tee -a $OUT
 # 2. C3 graph-mode substep time early / mid / late per switch
@@ -40,7 +40,7 @@ for cfg in "" "BENDY_SCAN_MT=1" "BENDY_SCAN_MT=1 BENDY_NARROW_DENSE=1"; do
 done
 # 4. compute-sanitizer on the variants (small scenes)
 for tool in memcheck racecheck; do
-  BENDY_TEST_UNPROVEN=1 timeout 900 compute-sanitizer --tool $tool python -m pytest tests/test_gpu_variants.py -m gpu -x -q \
+  BENDY_TEST_UNPROVEN=1 timeout 900 compute-sanitizer --tool $tool python -m pytest tests/test_z_gpu_variants.py -m gpu -x -q \
       -k "pool_flushes or 768 or strip_variants" > gpurun_out/r2_sanitizer_$tool.log 2>&1
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" gpurun_out/r2_sanitizer_$tool.log | tee -a $OUT
 done

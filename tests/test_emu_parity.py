@@ -73,5 +73,10 @@ def test_limits_strips_snapshot_golden_on_emulator(emu_lib):
 
 
 def test_opt_in_variants_on_emulator(emu_lib):
-    """the switches that are OFF by default (tests/test_gpu_variants.py): bit-identical to the default path"""
-    run_gpu_tests_on_emulator(emu_lib, ["tests/test_gpu_variants.py"])
+    """the switches that are OFF by default (tests/test_z_gpu_variants.py): bit-identical to the default path"""
+    run_gpu_tests_on_emulator(emu_lib, ["tests/test_z_gpu_variants.py"])
+
+
+def test_randomised_worlds_on_emulator(emu_lib):
+    """tests/test_z_gpu_fuzz.py: seeded random worlds mixing every feature, bit-exact where reference-pinned"""
+    run_gpu_tests_on_emulator(emu_lib, ["tests/test_z_gpu_fuzz.py"], extra_env={"BENDY_FUZZ_SEEDS": "120"})
