@@ -248,3 +248,72 @@ def test_overlapping_static_obstacles_follow_the_entry_candidate_rule():
         op, oq = o.particles()
         assert max_ulp(gp, op) == 0 and max_ulp(gq, oq) == 0, k
     assert (np.abs(gp - pts).max(1) > 0.05).sum() > 200  # the obstacles really pushed particles out
+
+
+# ------------------------------------------------------------------------------------------------
+# sessions: what a user does BETWEEN updates (the pub fields gravity / bounds are mutable, solver.rs:21-23;
+# add_* at any time, solver.rs:52-67; Clone, solver.rs:19) - every edit invalidates some cached device
+# state (graph, plan, params, grid), so the same random session runs on the device and on the oracle
+def _resync(g, o, info):
+    if g.get_particle_links():
+        o.set_link_order(g.link_order())
+    if info["radius"] > 0 and g.get_particle_len():
+        o.set_point_rank(g.point_rank())
+        o.set_grid(*g.grid())
+
+
+@pytest.mark.parametrize("seed", range(max(8, N_SEEDS // 3)))
+def test_random_session_matches_oracle(seed):
+    g, o, info = build_world(seed * 7 + 1, disable=("inv_mass",))
+    rng = np.random.default_rng(1000 + seed)
+    dt = float(f32(1.0 / 120.0) * f32(info["sub"]))
+    for step in range(14):
+        op = int(rng.integers(0, 8))
+        if op == 0:  # gravity is a pub field
+            gv = rng.uniform(-150, 150, 2).astype(f32)
+            g.gravity = gv
+            o.set_gravity(float(gv[0]), float(gv[1]))
+        elif op == 1:  # so are the bounds: shrink / shift them over the bodies
+            b = g.bounds
+            b.pos[:] = (b.pos + rng.uniform(-1, 2, 2)).astype(f32)
+            b.size[:] = np.maximum(b.size * rng.uniform(0.85, 1.05), 6.0).astype(f32)
+            o.set_bounds(float(b.pos[0]), float(b.pos[1]), float(b.size[0]), float(b.size[1]))
+            _resync(g, o, info)  # the broadphase grid follows the bounds
+        elif op == 2:  # a new particle, linked to an old one when there is one
+            n = g.get_particle_len()
+            p = (g.bounds.pos + g.bounds.size * rng.uniform(0.1, 0.9, 2)).astype(f32)
+            g.add_particle(p)
+            o.add_particle(float(p[0]), float(p[1]))
+            if n:
+                a = int(rng.integers(0, n))
+                L = float(f32(rng.uniform(0.5, 6.0)))
+                g.add_particle_link(ParticleLink(Link(a, n, L)))
+                o.add_particle_link(a, n, L)
+            _resync(g, o, info)
+        elif op == 3:  # a circle that was pushed before it was added (pending acc, particle.rs:48-54)
+            c = Circle(Particle((g.bounds.pos + g.bounds.size * rng.uniform(0.2, 0.8, 2)).astype(f32)), float(f32(rng.uniform(0.2, 2.0))))
+            fx, fy = (float(v) for v in rng.uniform(-400, 400, 2).astype(f32))
+            c.point.add_force(fx, fy)
+            g.add_circle(c)
+            o.add_circle([float(c.point.pos[0]), float(c.point.pos[1])], float(c.radius), acc=(fx, fy))
+            info["nC"] += 1
+        elif op == 4:  # Clone: the copy carries on, the original is dropped
+            g, o = g.clone(), o.clone()
+            _resync(g, o, info)
+        elif op == 5 and g.get_particle_len():  # the user overwrites some state (host buffers in, C ABI)
+            gp, gq = g.read_particles()
+            gp = (gp + rng.uniform(-0.05, 0.05, gp.shape)).astype(f32)
+            g.write_particles(gp, gq)
+            o.write_particles(gp, gq)
+        n_upd = int(rng.integers(1, 4))
+        g.update(dt, n=n_upd)
+        for _ in range(n_upd):
+            o.update(dt)
+        try:
+            st = compare_state(g, o, info["scale"], 1e-5, what=f"session {seed} step {step} op {op} {info}")
+        except BendyError as e:
+            if info["contact"] and "polygon broadphase overflow" in str(e):
+                pytest.skip("documented limit of the particle-polygon extension")
+            raise
+        if info["exact"]:
+            assert all(v == 0 for v in st.values()), (seed, step, op, st)
