@@ -92,6 +92,7 @@ extern "C" {
     pub fn bendy_get_kernel_times(s: *mut bendy_solver, ms: *mut f64, launches: *mut u64, n_classes: c_int,
                                   reset: c_int) -> c_int;
     pub fn bendy_launch_count(s: *const bendy_solver) -> u64;
+    pub fn bendy_get_stats(s: *mut bendy_solver, out: *mut u64, n: c_int) -> c_int;
     pub fn bendy_timer_start(s: *mut bendy_solver) -> c_int;
     pub fn bendy_timer_stop(s: *mut bendy_solver, ms: *mut c_float) -> c_int;
     pub fn bendy_get_stream(s: *const bendy_solver) -> *mut c_void;

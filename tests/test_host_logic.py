@@ -146,3 +146,26 @@ def test_header_is_plain_c_and_every_entry_point_links(tmp_path):
     # runs anywhere: without a GPU it stops after bendy_create fails loudly
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_rust_sys_crate_declares_the_header_symbol_for_symbol():
+    """The Rust -sys crate cannot be compiled in this image (no cargo/rustc), so at least keep its extern
+    block in step with include/bendy2d_b200.h: same symbol set, same number of parameters per function."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "bendy2d_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    rust = open(os.path.join(root, "rust", "bendy2d-sys", "src", "lib.rs")).read()
+    rust = re.sub(r"//[^\n]*", "", rust)
+
+    def arity(params):
+        params = params.strip()
+        return 0 if params in ("", "void") else params.count(",") + 1
+
+    c_decl = {m.group(1): arity(m.group(2)) for m in re.finditer(r"\b(bendy_\w+)\s*\(([^()]*)\)\s*;", header)}
+    r_decl = {m.group(1): arity(m.group(2)) for m in re.finditer(r"pub fn (bendy_\w+)\s*\(([^()]*)\)", rust)}
+    assert len(c_decl) >= 58
+    assert set(c_decl) == set(r_decl), (sorted(set(c_decl) - set(r_decl)), sorted(set(r_decl) - set(c_decl)))
+    wrong = {k: (c_decl[k], r_decl[k]) for k in c_decl if c_decl[k] != r_decl[k]}
+    assert not wrong, wrong
