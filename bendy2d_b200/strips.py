@@ -170,6 +170,49 @@ class _StripBase:
         return _halo_stats(self.solver)
 
 
+def gather_global_state(dist, world: int, device_index: int, global_index: np.ndarray, pos: np.ndarray,
+                        prev: np.ndarray, n_total: int):
+    """Every rank contributes the (pos, prev) of the particles it owns and receives the whole scene in
+    USER order.  Host-side and rare (rebalancing); float32 values travel bit-exactly as raw int32 words.
+    Works on whatever the process group's backend moves (CUDA tensors under nccl, CPU tensors under gloo)."""
+    import torch
+
+    dev = f"cuda:{device_index}" if world > 1 and dist.get_backend() == "nccl" else "cpu"
+    m_local = len(global_index)
+    cnt = torch.tensor([m_local], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(cnts, cnt)
+    else:
+        cnts = [cnt]
+    m = int(max(c.item() for c in cnts))
+    pack = torch.zeros((m, 6), dtype=torch.int32, device=dev)
+    words = np.empty((m_local, 6), np.int32)
+    gi = np.asarray(global_index, np.int64)
+    words[:, 0] = (gi & 0x7FFFFFFF).astype(np.int32)
+    words[:, 1] = (gi >> 31).astype(np.int32)
+    words[:, 2:4] = np.ascontiguousarray(pos, f32).view(np.int32).reshape(-1, 2)
+    words[:, 4:6] = np.ascontiguousarray(prev, f32).view(np.int32).reshape(-1, 2)
+    pack[:m_local] = torch.from_numpy(words).to(dev)
+    packs = [torch.zeros_like(pack) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(packs, pack)
+    else:
+        packs = [pack]
+    gpos, gprev = np.empty((n_total, 2), f32), np.empty((n_total, 2), f32)
+    seen = np.zeros(n_total, np.int32)
+    for c, pk in zip(cnts, packs):
+        a = pk[: int(c.item())].cpu().numpy()
+        idx = a[:, 0].astype(np.int64) | (a[:, 1].astype(np.int64) << 31)
+        gpos[idx] = np.ascontiguousarray(a[:, 2:4]).view(f32)
+        gprev[idx] = np.ascontiguousarray(a[:, 4:6]).view(f32)
+        seen[idx] += 1
+    if not (seen == 1).all():
+        raise HaloError(f"rebalance: {int((seen == 0).sum())} particles owned by no rank, "
+                        f"{int((seen > 1).sum())} owned by several")
+    return gpos, gprev
+
+
 class StripSolver(_StripBase):
     """One strip per process / GPU; halo over NCCL issued by the C library on its own stream."""
 
@@ -222,7 +265,8 @@ class StripSolver(_StripBase):
     def needs_rebalance(self) -> bool:
         import torch
 
-        flag = torch.tensor([1 if self.halo_stats()[3] else 0], device=f"cuda:{self.device_index}")
+        on_gpu = self.world > 1 and self.dist.get_backend() == "nccl"
+        flag = torch.tensor([1 if self.halo_stats()[3] else 0], device=f"cuda:{self.device_index}" if on_gpu else "cpu")
         if self.world > 1:
             self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX)
         return bool(flag.item())
@@ -231,26 +275,9 @@ class StripSolver(_StripBase):
         """Re-partition by the CURRENT positions: every rank gathers the full state (rare, host side),
         cuts new strips of equal body count and rebuilds its local solver; pos and prev travel
         bit-exactly, so the trajectory is unchanged."""
-        import torch
-
-        n = self.full_scene.n_particles
         pos, prev = self.solver.read_particles()
-        dev = f"cuda:{self.device_index}"
-        cnt = torch.tensor([len(pos)], device=dev)
-        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
-        self.dist.all_gather(cnts, cnt)
-        m = int(max(c.item() for c in cnts))
-        pack = torch.zeros((m, 5), dtype=torch.float64, device=dev)
-        pack[: len(pos), 0] = torch.from_numpy(self.part.global_index.astype(np.float64)).to(dev)
-        pack[: len(pos), 1:3] = torch.from_numpy(pos.astype(np.float64)).to(dev)
-        pack[: len(pos), 3:5] = torch.from_numpy(prev.astype(np.float64)).to(dev)
-        packs = [torch.zeros_like(pack) for _ in range(self.world)]
-        self.dist.all_gather(packs, pack)
-        gpos, gprev = np.empty((n, 2), f32), np.empty((n, 2), f32)
-        for c, pk in zip(cnts, packs):
-            a = pk[: int(c.item())].cpu().numpy()
-            idx = a[:, 0].astype(np.int64)
-            gpos[idx], gprev[idx] = a[:, 1:3].astype(f32), a[:, 3:5].astype(f32)
+        gpos, gprev = gather_global_state(self.dist, self.world, self.device_index, self.part.global_index, pos, prev,
+                                          self.full_scene.n_particles)
         self.solver = None
         self._build(replace(self.full_scene, particles=gpos), gprev)
 

@@ -107,3 +107,51 @@ def test_halo_bands_cover_all_contacts_gloo_world2():
     for rank, missing, n_ghost in res:
         assert missing == 0, f"rank {rank}: {missing} contact partners not covered by the halo"
         assert n_ghost > 0
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 10007
+    rng = np.random.default_rng(11)  # same stream on every rank
+    pos = rng.uniform(-50, 50, (n, 2)).astype(f32)
+    prev = rng.uniform(-50, 50, (n, 2)).astype(f32)
+    pos[5] = [np.nan, -0.0]
+    prev[9] = [np.inf, 1e-42]  # a denormal must survive too
+    owner = rng.integers(0, world, n)
+    owner[:100] = 0  # uneven shares
+    mine = np.nonzero(owner == rank)[0]
+    mine = mine[rng.permutation(len(mine))]  # the local (internal) order is not the user order
+    gpos, gprev = strips.gather_global_state(dist, world, 0, mine, pos[mine], prev[mine], n)
+    ok = np.array_equal(gpos.view(np.uint32), pos.view(np.uint32)) and np.array_equal(gprev.view(np.uint32), prev.view(np.uint32))
+    # a particle nobody owns / two owners must be reported, not silently filled with garbage
+    bad = mine[1:] if rank == 0 else mine
+    try:
+        strips.gather_global_state(dist, world, 0, bad, pos[bad], prev[bad], n)
+        caught = False
+    except strips.HaloError:
+        caught = True
+    q.put((rank, ok, caught))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_rebalance_gather_is_bit_exact_gloo(world):
+    """StripSolver.rebalance() re-partitions from the gathered global state: the gather (the part that needs
+    the process group) on CPU tensors under gloo, uneven shares, shuffled local order, NaN / -0 / denormals"""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok and caught for _, ok, caught in res), res
