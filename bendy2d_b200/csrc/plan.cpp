@@ -145,36 +145,45 @@ bool plan_links(size_t n_points, const uint32_t *ab, const float *len, size_t n_
         for (uint32_t i = P.part_start[p]; i < P.part_start[p + 1]; i++) part_of[i] = p;
 
     // ---- 3. colour: local links per partition, global links over the whole graph (user order)
+    // A link that finds no free local colour (its partition's 255-entry table is full: a point with more
+    // than ~128 links) is scheduled with the cross-partition links instead, and a cross-partition link
+    // that finds none of the 256 mask colours free gets an EXTRA colour: every vertex remembers the first
+    // extra colour it has not used yet, and the link takes the larger of its two ends' (so the links at a
+    // vertex get strictly increasing colours, which is all a colouring needs).  The reference relaxes any
+    // graph (solver.rs:144-146); so does this schedule - a hub of degree d costs about d launches.
     std::vector<ColourMask> lmask(n_linked), gmask;
+    std::vector<uint32_t> gnext;  // per vertex: first extra global colour (>= 256) not used at it yet
     std::vector<uint32_t> colour(n_links);
     std::vector<uint8_t> is_global(n_links, 0);
     uint32_t C = 0, G = 0;
     size_t n_global = 0;
+    (void)err;
     for (size_t k = 0; k < n_links; k++) {
         uint32_t a = P.rank[ab[2 * k]], b = P.rank[ab[2 * k + 1]];
+        int c = -1;
         if (part_of[a] == part_of[b]) {
-            int c = lowest_free(lmask[a], lmask[b]);
-            if (c < 0 || c >= (int)kMaxLocalColours) {
-                // greedy edge colouring needs at most 2*degree-1 colours: degree <= 128 always fits
-                if (err)
-                    *err = "link planner: more than 255 link colours needed inside one partition (a point with more "
-                           "than 128 links can cause this)";
-                return false;
-            }
+            c = lowest_free(lmask[a], lmask[b]);
+            if (c >= (int)kMaxLocalColours) c = -1;
+        }
+        if (c >= 0) {
             mark(lmask[a], c), mark(lmask[b], c);
             colour[k] = (uint32_t)c;
             C = std::max(C, (uint32_t)c + 1);
         } else {
             if (gmask.empty()) gmask.resize(n_linked);
-            int c = lowest_free(gmask[a], gmask[b]);
-            if (c < 0) {
-                if (err) *err = "link planner: more than 256 colours needed for the cross-partition links";
-                return false;
+            uint32_t gc;
+            c = lowest_free(gmask[a], gmask[b]);
+            if (c >= 0) {
+                mark(gmask[a], c), mark(gmask[b], c);
+                gc = (uint32_t)c;
+            } else {
+                if (gnext.empty()) gnext.assign(n_linked, 256u);
+                gc = std::max(gnext[a], gnext[b]);
+                gnext[a] = gnext[b] = gc + 1;
             }
-            mark(gmask[a], c), mark(gmask[b], c);
-            colour[k] = (uint32_t)c;
+            colour[k] = gc;
             is_global[k] = 1;
-            G = std::max(G, (uint32_t)c + 1);
+            G = std::max(G, gc + 1);
             n_global++;
         }
     }

@@ -130,7 +130,7 @@ int bendy_set_plan_params(bendy_solver *s, uint32_t pack_points, uint32_t max_po
 typedef struct bendy_schedule_info {
     uint32_t n_partitions;      /* shared-memory link partitions (free particles) */
     uint32_t n_local_colours;   /* max colours inside one partition */
-    uint32_t n_global_colours;  /* colours of cross-partition links (one launch each) */
+    uint32_t n_global_colours;  /* colours of cross-partition links and of links that found no local colour (one launch each) */
     uint32_t n_local_links;
     uint32_t n_global_links;
     uint32_t n_poly_partitions; /* partitions holding polygon-internal links */

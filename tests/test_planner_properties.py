@@ -23,7 +23,7 @@ def check_schedule(n, ab, pack, maxp):
     r = rank.astype(np.int64)
     local = part != GLOBAL
     # 1. every bucket is an independent edge set
-    key = np.where(local, part.astype(np.int64), -1) * 1024 + colour
+    key = np.where(local, part.astype(np.int64), -1) * (1 << 32) + colour
     for k in np.unique(key):
         ends = ab[key == k].ravel()
         assert len(np.unique(ends)) == len(ends)
@@ -36,13 +36,15 @@ def check_schedule(n, ab, pack, maxp):
     spans.sort()
     for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
         assert a1 < b0
-    # 3. a global link really crosses two partitions' ranges (otherwise it should have been local)
+    # 3. a global link really crosses two partitions' ranges (otherwise it should have been local), unless the
+    # 255 local colours of its partition were used up at one of its ends (a hub)
     if spans and (~local).any():
         lo = np.array([s[0] for s in spans])
+        deg = np.bincount(ab.ravel(), minlength=n)
         for a, b in ab[~local]:
             ia, ib = np.searchsorted(lo, r[a], "right"), np.searchsorted(lo, r[b], "right")
-            assert ia != ib or not (spans[ia - 1][0] <= r[a] <= spans[ia - 1][1] and
-                                    spans[ib - 1][0] <= r[b] <= spans[ib - 1][1])
+            assert ia != ib or max(deg[a], deg[b]) > 128 or not (spans[ia - 1][0] <= r[a] <= spans[ia - 1][1] and
+                                                                 spans[ib - 1][0] <= r[b] <= spans[ib - 1][1])
     # 4. the exported order is partition-major, colour-major, global colours last
     is_glob = ~local[perm]
     assert (np.diff(is_glob.astype(int)) >= 0).all()
@@ -127,17 +129,19 @@ def test_bucket_parallel_relaxation_equals_the_sequential_walk(g):
     assert np.array_equal(seq.view(np.uint32), par.view(np.uint32))
 
 
-def test_colour_limit_is_the_kernels_table_size():
-    # a star of degree d needs exactly d colours; the partition kernel holds 255 (kernels.cuh K3_MAX_COLOURS)
-    for deg, ok in ((128, True), (255, True), (256, False), (400, False)):
+def test_hubs_beyond_the_colour_tables_spill_into_extra_global_colours():
+    # a star of degree d needs exactly d colours; the partition kernel's table holds 255 (kernels.cuh
+    # K3_MAX_COLOURS), the cross-partition masks another 256; whatever is left gets one extra colour each.
+    # The reference relaxes any graph (solver.rs:144-146), so the planner must never refuse one.
+    for deg in (128, 255, 256, 400, 511, 512, 2000):
         ab = [[0, i] for i in range(1, deg + 1)]
-        if ok:
-            info = plan_links(deg + 1, ab)[4]
-            assert info["n_local_colours"] == deg
-        else:
-            with pytest.raises(BendyError) as e:
-                plan_links(deg + 1, ab)
-            assert not isinstance(e.value, LinkPanic) and "colours" in str(e.value)
+        rank, perm, colour, part, info = check_schedule(deg + 1, ab, 0, 0)
+        assert info["n_local_colours"] == min(deg, 255)
+        assert info["n_global_links"] == max(0, deg - 255)
+        assert info["n_global_colours"] == max(0, deg - 255)
+    # two hubs sharing their leaves, in a partition that also holds ordinary links
+    ab = [[0, i] for i in range(2, 700)] + [[1, i] for i in range(2, 700)] + [[i, i + 1] for i in range(2, 699)]
+    check_schedule(700, ab, 0, 0)
 
 
 def test_empty_and_degenerate_inputs():

@@ -317,3 +317,31 @@ def test_random_session_matches_oracle(seed):
             raise
         if info["exact"]:
             assert all(v == 0 for v in st.values()), (seed, step, op, st)
+
+
+@pytest.mark.parametrize("deg", [300, 900])
+def test_hub_with_more_links_than_the_colour_tables_hold(deg):
+    """One particle tied to `deg` others (the partition kernel has 255 colours, the cross-partition masks 256
+    more): the links that find no colour get extra colours of their own and the schedule is still an
+    order of the reference's sequential walk (solver.rs:144-146) - bit-exact against the oracle replay."""
+    rng = np.random.default_rng(deg)
+    n = deg + 40
+    pos = np.stack([rng.uniform(20, 80, n), rng.uniform(10, 60, n)], 1).astype(f32)
+    ab = [[0, i] for i in range(1, deg + 1)] + [[i, i + 1] for i in range(1, n - 1)] + [[3, n - 1], [0, n - 2]]
+    ab = np.array(ab, np.uint32)[rng.permutation(len(ab))]
+    d = np.linalg.norm(pos[ab[:, 0]].astype(np.float64) - pos[ab[:, 1]], axis=1)
+    ln = (d * rng.uniform(0.9, 1.1, len(ab))).astype(f32)
+    g, o = Solver(), bo.OracleSolver()
+    g.add_particles(pos)
+    o.add_particles(pos)
+    g.add_particle_links(ab, ln)
+    o.add_particle_links(ab, ln)
+    info = g.schedule_info()
+    assert info["n_local_colours"] == 255 and info["n_global_links"] >= deg - 255
+    o.set_link_order(g.link_order())
+    for k in range(8):
+        g.update(1 / 240)
+        o.update(1 / 240)
+        gp, gq = g.read_particles()
+        op, oq = o.particles()
+        assert max_ulp(gp, op) == 0 and max_ulp(gq, oq) == 0, k
