@@ -104,6 +104,10 @@ def build_world(seed, disable=()):
         crad = rng.uniform(0.05, 3.0, nC).astype(f32)
         if rng.uniform() < 0.2:
             crad[0] = 9.0
+        if rng.uniform() < 0.15:  # the reference takes any radius: zero and negative ones too (circle.rs:35-36)
+            odd = rng.uniform(size=nC)
+            crad[odd < 0.2] *= f32(-1.0)
+            crad[odd > 0.85] = 0.0
         g.add_circles(cpos, crad)
         for p, r in zip(cpos, crad):
             o.add_circle(p, float(r))
@@ -345,3 +349,22 @@ def test_hub_with_more_links_than_the_colour_tables_hold(deg):
         gp, gq = g.read_particles()
         op, oq = o.particles()
         assert max_ulp(gp, op) == 0 and max_ulp(gq, oq) == 0, k
+
+
+def test_negative_radius_outside_the_near_band_is_still_resolved():
+    """circle.rs:35-36 squares the radius sum, so r1 + r2 = -1.2 overlaps up to distance 1.2.  The parallel
+    circle pass certifies itself with a gap argument that needs non-negative radii: a pair at distance 1.18
+    (inside 1.2, outside |-1.2 + r_min|) was skipped until the pass learnt to take the plain path here."""
+    g, o = Solver(), bo.OracleSolver()
+    g.gravity = np.zeros(2, f32)
+    o.set_gravity(0.0, 0.0)
+    pos = np.array([[20, 20], [21.18, 20], [60, 60]], f32)
+    rad = np.array([-1.5, 0.3, 0.05], f32)
+    g.add_circles(pos, rad)
+    for p, r in zip(pos, rad):
+        o.add_circle(p, float(r))
+    for _ in range(3):
+        g.update(1 / 120)
+        o.update(1 / 120)
+        assert max_ulp(g.read_circles()[0], o.circles()[0]) == 0
+    assert abs(g.read_circles()[0][1, 0] - 21.18) > 1.0  # the pair really was resolved
