@@ -22,6 +22,25 @@ N_SEEDS = int(os.environ.get("BENDY_FUZZ_SEEDS", "24"))
 N_UPDATES = int(os.environ.get("BENDY_FUZZ_UPDATES", "12"))
 
 
+def odd_polygon(rng, cx, cy):
+    """what Polygon::new accepts without complaint (polygon.rs:84-123): any point list"""
+    kind = int(rng.integers(0, 4))
+    if kind == 0:  # a point cloud in drawing order: non-convex, usually self-intersecting
+        n = int(rng.integers(3, 8))
+        return (np.array([cx, cy]) + rng.uniform(-3.0, 3.0, (n, 2))).astype(f32)
+    if kind == 1:  # more vertices than the per-thread local copy of the prepare kernel holds (16)
+        n = int(rng.integers(17, 31))
+        th = 2 * np.pi * np.arange(n) / n
+        r = rng.uniform(1.5, 4.0)
+        return np.stack([cx + r * np.cos(th), cy + r * np.sin(th)], 1).astype(f32)
+    pts = convex_ngon(rng, cx, cy)
+    if kind == 2:  # a repeated vertex: a zero-length edge, NaN normals exactly like the reference
+        pts = np.concatenate([pts[:2], pts[1:]])
+    else:  # collinear run
+        pts = np.concatenate([pts[:1], ((pts[0] + pts[1]) / 2)[None].astype(f32), pts[1:]])
+    return pts
+
+
 def convex_ngon(rng, cx, cy):
     n = int(rng.integers(3, 10))
     r = rng.uniform(0.8, 4.0)
@@ -125,8 +144,12 @@ def build_world(seed, disable=()):
     any_static = False
     if "polygons" in disable:
         nG = 0
+    odd_polys = rng.uniform() < 0.3
     for k in range(nG):
-        pts = convex_ngon(rng, centres[k, 0], centres[k, 1])
+        if odd_polys and rng.uniform() < 0.5:
+            pts = odd_polygon(rng, centres[k, 0], centres[k, 1])
+        else:
+            pts = convex_ngon(rng, centres[k, 0], centres[k, 1])
         st = bool(rng.uniform() < 0.4)
         any_static |= st
         g.add_polygon(Polygon.new(pts, st))
