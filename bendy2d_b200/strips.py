@@ -51,6 +51,8 @@ class StripPart:
     x_right: float
     band: float
     ghost_cap: int
+    stray_margin_left: Optional[float] = None   # how far an owned disc may sit inside the left / right neighbour
+    stray_margin_right: Optional[float] = None  # before the ownership counts as stale (None = band / 2)
 
     @property
     def send_left_below(self) -> float:   # owned discs with x below this go to the left neighbour
@@ -60,15 +62,18 @@ class StripPart:
     def send_right_above(self) -> float:
         return float(self.x_right - self.band) if np.isfinite(self.x_right) else float("inf")
 
-    # an owned disc further than band/2 inside a neighbour's strip makes the ownership stale: as long
-    # as nothing moves more than band/2 - 2r between two checks, no contact can have been missed
+    # an owned disc further than the stray margin (band/2, less next to a narrow strip: see partition_scene)
+    # inside a neighbour's strip makes the ownership stale: as long as nothing moves more than the margin
+    # - 2r between two checks, no contact can have been missed
     @property
     def stray_left(self) -> float:
-        return float(self.x_left - 0.5 * self.band) if np.isfinite(self.x_left) else float("-inf")
+        m = self.stray_margin_left if self.stray_margin_left is not None else 0.5 * self.band
+        return float(self.x_left - m) if np.isfinite(self.x_left) else float("-inf")
 
     @property
     def stray_right(self) -> float:
-        return float(self.x_right + 0.5 * self.band) if np.isfinite(self.x_right) else float("inf")
+        m = self.stray_margin_right if self.stray_margin_right is not None else 0.5 * self.band
+        return float(self.x_right + m) if np.isfinite(self.x_right) else float("inf")
 
 
 def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodies: Optional[np.ndarray] = None,
@@ -82,12 +87,17 @@ def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodi
         bodies = scene.body_of if scene.body_of is not None else body_ids(scene)
     bodies = np.asarray(bodies, np.int64)
     nb = int(bodies.max()) + 1 if n else 0
-    cnt = np.bincount(bodies, minlength=nb).astype(np.float64)
-    cx = np.bincount(bodies, weights=scene.particles[:, 0].astype(np.float64), minlength=nb) / np.maximum(cnt, 1)
+    # non-finite positions are legal state (coincident points give NaN in the reference too, link.rs:24):
+    # they take no part in the geometry of the cut; a body without any finite point sits at x = 0
+    px = scene.particles[:, 0].astype(np.float64)
+    fin = np.isfinite(px)
+    cnt = np.bincount(bodies[fin], minlength=nb).astype(np.float64)
+    cx = np.bincount(bodies[fin], weights=px[fin], minlength=nb) / np.maximum(cnt, 1)
     xmin = np.full(nb, np.inf)
     xmax = np.full(nb, -np.inf)
-    np.minimum.at(xmin, bodies, scene.particles[:, 0])
-    np.maximum.at(xmax, bodies, scene.particles[:, 0])
+    np.minimum.at(xmin, bodies[fin], px[fin])
+    np.maximum.at(xmax, bodies[fin], px[fin])
+    xmin[cnt == 0] = xmax[cnt == 0] = 0.0
     order = np.argsort(cx, kind="stable")
     # equal body counts per strip; edge = midway between the neighbouring groups' centroids
     cuts = [int(round(k * nb / world)) for k in range(world + 1)]
@@ -105,6 +115,18 @@ def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodi
         # band/2 before the ownership is rebalanced; + drift allowance + contact range
         half = 0.5 * float(np.max(xmax - xmin)) if nb else 0.0
         band = 2.0 * half + 2.0 + 2.0 * scene.particle_radius
+    # The exchange only reaches the two neighbours.  A disc owned by strip k-1 may sit up to its stray margin
+    # inside strip k before the ownership counts as stale, and so may one of strip k+1 from the other side; the
+    # two must not be able to touch (2r) without either owner seeing the other, so next to a strip narrower than
+    # band + 2r the margins shrink to half of what the narrow strip leaves: m = min(band/2, (width_k - 2r)/2).
+    r2 = 2.0 * scene.particle_radius
+    margin_into = [0.5 * band] * world  # margin_into[k]: how far a neighbour's disc may sit inside strip k
+    for k in range(1, world - 1):
+        width = edges[k + 1] - edges[k]
+        margin_into[k] = min(0.5 * band, 0.5 * (width - r2))
+        if not margin_into[k] > r2:
+            raise ValueError(f"strip {k} of {world} is {width:.3f} wide: too narrow to keep the discs of strips {k - 1} and "
+                             f"{k + 1} apart (contact range {r2:.3f}); use fewer strips")
     strip_of_particle = strip_of_body[bodies]
     parts = []
     link_strip = strip_of_particle[scene.links_ab[:, 0].astype(np.int64)] if scene.n_links else np.zeros(0, np.int64)
@@ -125,7 +147,9 @@ def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodi
             in_band = max(in_band, int((px < xl + band).sum()))
         if np.isfinite(xr):
             in_band = max(in_band, int((px > xr - band).sum()))
-        parts.append(StripPart(k, world, local, sel, float(xl), float(xr), float(band), 0 if world == 1 else in_band))
+        parts.append(StripPart(k, world, local, sel, float(xl), float(xr), float(band), 0 if world == 1 else in_band,
+                               float(margin_into[k - 1]) if k > 0 else None,
+                               float(margin_into[k + 1]) if k + 1 < world else None))
     # both ends of an exchange use the same message size: one capacity for the whole chain
     cap = int(max(p.ghost_cap for p in parts) * cap_factor) + 1024 if world > 1 else 0
     for p in parts:

@@ -26,7 +26,9 @@ def touching_field(nx=8, ny=3):
 
 @pytest.mark.parametrize("n_strips", [2, 3, 5])
 def test_local_strip_group_is_bit_identical_to_single_solver(n_strips):
-    sc = touching_field()
+    # 5 strips need a wider field: next to a strip that holds a single column of bodies the stray margin
+    # shrinks below the half width of a body (strips.partition_scene) and the run would be flagged at once
+    sc = touching_field() if n_strips < 5 else touching_field(16, 2)
     ref = Solver()
     sc.load_into(ref)
     grp = strips.LocalStripGroup(sc, n_strips)
@@ -41,7 +43,7 @@ def test_local_strip_group_is_bit_identical_to_single_solver(n_strips):
     assert sum(a + b for a, b, _, _ in stats) > 0, "no halo traffic: the test scene does not exercise the exchange"
     # contacts across strip edges really happened: positions differ from a run without collisions
     free = Solver()
-    sc2 = touching_field()
+    sc2 = touching_field() if n_strips < 5 else touching_field(16, 2)
     sc2.particle_radius = 0.0
     sc2.load_into(free)
     free.update(sc.dt, n=60)

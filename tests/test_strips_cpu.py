@@ -155,3 +155,27 @@ def test_rebalance_gather_is_bit_exact_gloo(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok and caught for _, ok, caught in res), res
+
+
+def test_stray_margins_shrink_next_to_a_narrow_strip_and_too_narrow_strips_are_refused():
+    """The exchange only reaches the two neighbours, so the discs of strips k-1 and k+1 must never be able to
+    touch inside strip k: next to a narrow strip the stray margins shrink to half of what it leaves, and a
+    strip that cannot keep them 2r apart is refused (found by the randomised strip fields: two bodies owned
+    by strips 1 and 3 touched inside a 1.6-wide strip 2 and neither owner saw the other)."""
+    sc = small_field()  # columns of bodies 4.9 apart, default band 6.95
+    parts = strips.partition_scene(sc, 8)
+    r2 = 2 * sc.particle_radius
+    for k, p in enumerate(parts):
+        assert (p.stray_margin_left is None) == (k == 0) and (p.stray_margin_right is None) == (k == 7)
+    for a, b, c in zip(parts, parts[1:], parts[2:]):  # a strays right into b, c strays left into b
+        width = b.x_right - b.x_left
+        assert a.stray_margin_right == c.stray_margin_left == min(0.5 * b.band, 0.5 * (width - r2))
+        assert (a.stray_right - b.x_left) + (b.x_right - c.stray_left) + r2 <= width + 1e-9
+    # wide strips keep band / 2 (the 16M benchmark scene: strips 256 wide, band 6.95)
+    wide = strips.partition_scene(sc, 2)
+    assert wide[0].stray_right == wide[0].x_right + 0.5 * wide[0].band
+    # a strip narrower than the contact range cannot be protected at all
+    sc2 = scenes.c2_free_particles(40, 4)
+    sc2.particles[:, 0] = (10.0 + 0.001 * np.arange(sc2.n_particles)).astype(f32)  # 160 discs within 0.16
+    with pytest.raises(ValueError, match="too narrow"):
+        strips.partition_scene(sc2, 4, band=1.0)

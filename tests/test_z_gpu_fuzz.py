@@ -391,3 +391,72 @@ def test_negative_radius_outside_the_near_band_is_still_resolved():
         o.update(1 / 120)
         assert max_ulp(g.read_circles()[0], o.circles()[0]) == 0
     assert abs(g.read_circles()[0][1, 0] - 21.18) > 1.0  # the pair really was resolved
+
+
+# ------------------------------------------------------------------------------------------------
+# strips: random fields of small bodies cut into 2..6 strips must reproduce the unsharded run bit for bit
+@pytest.mark.parametrize("seed", range(max(6, N_SEEDS // 4)))
+def test_random_strip_field_is_bit_identical_to_single_solver(seed):
+    from bendy2d_b200 import scenes, strips
+
+    rng = np.random.default_rng(5000 + seed)
+    n_bodies = int(rng.integers(6, 40))
+    W = float(rng.uniform(30, 70))
+    pts, ab, ln, body = [], [], [], []
+    base = 0
+    for b in range(n_bodies):
+        w, h = int(rng.integers(2, 7)), int(rng.integers(2, 7))
+        d = 0.25
+        ox, oy = rng.uniform(1, W - 3), rng.uniform(1, 10)
+        ix, iy = np.meshgrid(np.arange(w), np.arange(h))
+        p = np.stack([ox + d * ix.ravel(), oy + d * iy.ravel()], 1)
+        idx = base + np.arange(w * h).reshape(h, w)
+        e = np.concatenate([np.stack([idx[:, :-1].ravel(), idx[:, 1:].ravel()], 1),
+                            np.stack([idx[:-1].ravel(), idx[1:].ravel()], 1),
+                            np.stack([idx[:-1, :-1].ravel(), idx[1:, 1:].ravel()], 1)])
+        pts.append(p), ab.append(e), body.append(np.full(w * h, b))
+        ln.append(np.linalg.norm(p[e[:, 0] - base] - p[e[:, 1] - base], axis=1))
+        base += w * h
+    sc = scenes.Scene(f"strip fuzz {seed}", (0.0, 0.0, W, 24.0), particle_radius=0.1,
+                      particles=np.concatenate(pts).astype(f32), links_ab=np.concatenate(ab).astype(np.uint32),
+                      links_len=np.concatenate(ln).astype(f32), body_of=np.concatenate(body))
+    sub = int(rng.choice([1, 2, 4]))
+    sc.sub_steps, sc.dt = sub, float(f32(sub / 120.0))
+    n_strips = int(rng.integers(2, 7))
+    ref = Solver()
+    sc.load_into(ref)
+    n_strips = min(n_strips, n_bodies)
+    while True:  # an interior strip must be wider than the contact range (the partitioner refuses otherwise)
+        try:
+            grp = strips.LocalStripGroup(sc, n_strips)
+            break
+        except ValueError as e:
+            assert "too narrow" in str(e) and n_strips > 2
+            n_strips -= 1
+    rebalanced = 0
+    band = grp.parts[0].band
+    before = ref.read_particles()[0]
+    for k in range(120 // sub):
+        ref.update(sc.dt)
+        grp.update(sc.dt)
+        # the ownership contract (strips.StripPart): between two polls of the stray flag nothing may move
+        # further than band/2 - 2r, or a contact can be missed before the flag is seen.  Bodies that were
+        # generated on top of each other fly apart faster than that: such a seed says nothing about strips.
+        after = ref.read_particles()[0]
+        with np.errstate(invalid="ignore"):
+            moved = np.nanmax(np.abs(after[:, 0] - before[:, 0]), initial=0.0)
+        margin = min([0.5 * band] + [m for p in grp.parts for m in (p.stray_margin_left, p.stray_margin_right) if m is not None])
+        if moved > margin - 2 * sc.particle_radius:
+            pytest.skip(f"a disc moved {moved:.2f} between two polls: outside the rebalance contract (band {band:.2f})")
+        before = after
+        if grp.needs_rebalance():
+            try:
+                grp.rebalance()
+            except ValueError as e:
+                assert "too narrow" in str(e)
+                pytest.skip("the bodies drifted into a layout that needs fewer strips")
+            rebalanced += 1
+    assert all(o == 0 for _, _, o, _ in grp.halo_stats()), grp.halo_stats()
+    gp, gq = grp.read_particles()
+    rp, rq = ref.read_particles()
+    assert max_ulp(gp, rp) == 0 and max_ulp(gq, rq) == 0, (seed, n_strips, n_bodies, rebalanced)
