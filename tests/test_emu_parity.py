@@ -79,4 +79,4 @@ def test_opt_in_variants_on_emulator(emu_lib):
 
 def test_randomised_worlds_on_emulator(emu_lib):
     """tests/test_z_gpu_fuzz.py: seeded random worlds mixing every feature, bit-exact where reference-pinned"""
-    run_gpu_tests_on_emulator(emu_lib, ["tests/test_z_gpu_fuzz.py"], extra_env={"BENDY_FUZZ_SEEDS": "120"})
+    run_gpu_tests_on_emulator(emu_lib, ["tests/test_z_gpu_fuzz.py"], extra_env={"BENDY_FUZZ_SEEDS": "60"})

@@ -290,12 +290,12 @@ def _resync(g, o, info):
 
 
 @pytest.mark.parametrize("seed", range(max(8, N_SEEDS // 3)))
-def test_random_session_matches_oracle(seed):
+def test_random_session_matches_oracle(seed, tmp_path):
     g, o, info = build_world(seed * 7 + 1, disable=("inv_mass",))
     rng = np.random.default_rng(1000 + seed)
     dt = float(f32(1.0 / 120.0) * f32(info["sub"]))
     for step in range(14):
-        op = int(rng.integers(0, 8))
+        op = int(rng.integers(0, 10))
         if op == 0:  # gravity is a pub field
             gv = rng.uniform(-150, 150, 2).astype(f32)
             g.gravity = gv
@@ -332,6 +332,22 @@ def test_random_session_matches_oracle(seed):
             gp = (gp + rng.uniform(-0.05, 0.05, gp.shape)).astype(f32)
             g.write_particles(gp, gq)
             o.write_particles(gp, gq)
+        elif op == 6:  # the solver goes to disk and comes back (raw SoA snapshot, the on-disk form of Clone)
+            path = str(tmp_path / f"s{step}.b2d")
+            g.save_snapshot(path)
+            old = g
+            g = Solver.load_snapshot(path)
+            # gravity / bounds are the caller's pub fields (solver.rs:21-22), handed to the C ABI with every
+            # update; the file only knows the values of the last update, so the caller carries its own over
+            g.gravity = old.gravity.copy()
+            g.bounds.pos[:] = old.bounds.pos
+            g.bounds.size[:] = old.bounds.size
+            _resync(g, o, info)
+        elif op == 7:  # sub_steps is private and fixed in the reference; here it may change between updates
+            info["sub"] = int(rng.choice([1, 2, 3]))
+            g.set_sub_steps(info["sub"])
+            o.set_sub_steps(info["sub"])
+            dt = float(f32(1.0 / 120.0) * f32(info["sub"]))
         n_upd = int(rng.integers(1, 4))
         g.update(dt, n=n_upd)
         for _ in range(n_upd):
