@@ -77,7 +77,10 @@ struct NcclApi {
     std::string err;
     bool load() {
         if (lib) return true;
-        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+        // BENDY_NCCL_LIB names the NCCL build to use (a path or a soname); default: the one already in the process
+        const char *user = getenv("BENDY_NCCL_LIB");
+        for (const char *name : {user, "libnccl.so.2", "libnccl.so"}) {
+            if (!name || !*name) continue;
             lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (lib) break;
         }

@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "bendy2d_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libbendy2d_b200_emu.so")
+NCCL_STUB = os.path.join(OUT, "libcuemu_nccl.so")
 
 _LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)\s*<<<(.+?)>>>\s*\(", re.S)
 _EXTERN_SHARED = re.compile(r"extern\s+__shared__\s+([\w ]+?)\s+(\w+)\s*\[\s*\]\s*;")
@@ -77,7 +78,7 @@ def transform(text: str, name: str) -> str:
 def build(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in ("solver.cu", "kernels.cuh", "plan.cpp", "plan.h")]
     deps = srcs + [os.path.join(HERE, "runtime.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"),
-                   os.path.join(HERE, "include", "nccl.h"), os.path.abspath(__file__),
+                   os.path.join(HERE, "include", "nccl.h"), os.path.join(HERE, "nccl_stub.cpp"), os.path.abspath(__file__),
                    os.path.join(ROOT, "include", "bendy2d_b200.h")]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(map(os.path.getmtime, deps)):
         return LIB
@@ -99,6 +100,9 @@ def build(force: bool = False) -> str:
     cmd = [cxx] + flags + ["-o", LIB, os.path.join(gen, "solver_emu.cpp"), os.path.join(gen, "plan.cpp"),
                            os.path.join(HERE, "runtime.cpp"), "-ldl"]
     subprocess.check_call(cmd)
+    # the NCCL entry points over FIFOs, for the multi-process strip tests (solver.cu finds it through BENDY_NCCL_LIB)
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-w", "-o", NCCL_STUB,
+                           os.path.join(HERE, "nccl_stub.cpp"), "-ldl"])
     return LIB
 
 

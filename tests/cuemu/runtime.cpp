@@ -307,6 +307,12 @@ void launch(const char *name, const void *fn_key, dim3 grid, dim3 block, size_t 
 
 using namespace cuemu;
 
+// host callback in stream order (recorded during capture, replayed with the graph): the NCCL stub's exchange
+extern "C" int cuemu_enqueue_host(void (*fn)(void *), void *arg) {
+    enqueue([fn, arg]() { fn(arg); });
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 const char *cudaGetErrorName(cudaError_t e) {
     switch (e) {

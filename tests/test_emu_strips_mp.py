@@ -1,0 +1,109 @@
+"""The multi-process strip path (bendy2d_b200.strips.StripSolver: one process per GPU, NCCL halo exchange issued
+inside the captured graph, rebalancing over the process group) WITHOUT GPUs: every rank process loads the CPU
+emulation build of the library (tests/cuemu) and a stub of the eight NCCL entry points that moves the messages
+over FIFOs (tests/cuemu/nccl_stub.cpp); torch.distributed runs on gloo.  Test infrastructure only; what it
+checks is the host logic of the N>1 path (partition, unique-id broadcast, communicator, send/recv inside the
+graph, stray detection, rebalance) and that the sharded run is bit-identical to the unsharded one.
+"""
+import os
+import shutil
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "cuemu"))
+
+pytestmark = pytest.mark.skipif(shutil.which(os.environ.get("CXX", "g++")) is None, reason="needs g++")
+f32 = np.float32
+
+
+def _worker(rank, world, port, case, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, HERE)
+    from bendy2d_b200 import Solver, _lib, scenes, strips
+    from test_gpu_strips import touching_field
+
+    assert _lib.LIB_PATH.endswith("_emu.so")
+    try:
+        if case == "bodies":
+            sc = touching_field() if world < 4 else touching_field(16, 2)
+            sv = strips.StripSolver(sc, rank, world, 0, dist)
+            for _ in range(3):
+                sv.update(sc.dt, n=20)
+                sent = sv.check_halo()
+            n_updates, rebalanced = 60, 0
+        else:  # free particles pile up and spread sideways: ownership has to follow (rebalance over the group)
+            sc = scenes.c2_free_particles(80, 30)
+            sc.bounds = (0.0, 0.0, 48.0, 12.0)
+            sv = strips.StripSolver(sc, rank, world, 0, dist, band=4.0)
+            n_updates, rebalanced, sent = 150, 0, (0, 0)
+            for _ in range(n_updates):
+                sv.update(sc.dt)
+                if sv.needs_rebalance():
+                    sv.rebalance()
+                    rebalanced += 1
+        pos, prev = sv.read_particles()
+        gpos, gprev = strips.gather_global_state(dist, world, 0, sv.part.global_index, pos, prev, sc.n_particles)
+        ok = True
+        if rank == 0:
+            ref = Solver()
+            sc.load_into(ref)
+            ref.update(sc.dt, n=n_updates)
+            rp, rq = ref.read_particles()
+            ok = np.array_equal(gpos.view(np.uint32), rp.view(np.uint32)) and np.array_equal(gprev.view(np.uint32), rq.view(np.uint32))
+        q.put((rank, ok, int(sum(sent)), rebalanced, sv.schedule_info()["kernels_per_substep"]))
+    except Exception as e:  # report instead of hanging the other ranks' queue reader
+        q.put((rank, False, repr(e), 0, 0))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, case, extra_env=None):
+    import build as cuemu_build
+    import torch.multiprocessing as mp
+
+    lib = cuemu_build.build()
+    env = {"BENDY2D_B200_LIB": lib, "BENDY_CUDA_EMU": "1", "BENDY_NCCL_LIB": cuemu_build.NCCL_STUB}
+    env.update(extra_env or {})
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = 33500 + (os.getpid() % 2000) + 7 * world + (11 if case == "bodies" else 0)
+        procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=600) for _ in procs]
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return sorted(res)
+
+
+@pytest.mark.parametrize("world,extra", [(2, {}), (3, {"BENDY_HALO_FUSED": "1", "BENDY_SCAN_MT": "1", "BENDY_NARROW_DENSE": "1"}),
+                                         (4, {"BENDY_HALO_OVERLAP": "1"})])
+def test_nccl_strip_solvers_match_the_single_solver_bit_for_bit(world, extra):
+    res = _run(world, "bodies", extra)
+    assert all(ok is True for _, ok, *_ in res), res
+    assert sum(r[2] for r in res) > 0, "no halo traffic: the scene does not exercise the exchange"
+    assert all(r[4] > 0 for r in res), "the substeps did not run as a captured graph"
+
+
+def test_nccl_strip_solvers_rebalance_over_the_process_group():
+    res = _run(3, "free")
+    assert all(ok is True for _, ok, *_ in res), res
+    assert res[0][3] > 0, "the scene never needed rebalancing: nothing was tested"
