@@ -169,6 +169,9 @@ struct bendy_solver {
     DevBuf<uint32_t> d_cell_count, d_cell_start, d_tile_sum, d_sorted_id, d_slot_of;
     DevBuf<uint32_t> d_scan_barrier;
     uint32_t scan_fused_capacity = 0;  // CTAs of k2_scan_fused that can be resident at once
+    bool sort_fused = false;           // BENDY_SORT_FUSED=1: k2_scan_scatter_fused (scan + scatter in one launch)
+    uint32_t sort_fused_capacity = 0;
+    bool scatter_ilp = false;          // BENDY_SCATTER_ILP=1: k2_scatter_ilp (4 discs per thread)
     bool halo_fused = false;           // BENDY_HALO_FUSED=1: send-buffer reset + ghost histogram in one launch
     bool narrow_dense = false;         // BENDY_NARROW_DENSE=1: k2_narrow_dense (lane-dense contact resolution)
     bool scan_mt = false;              // BENDY_SCAN_MT=1: k2_scan_fused_mt<2|4> when one tile per CTA does not fit
@@ -703,8 +706,8 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
             CK(s->d_cell_count.ensure(padded));
             CK(cudaMemsetAsync(s->d_cell_count.p, 0, padded * sizeof(uint32_t), s->stream));
             CK(s->d_cell_start.ensure(padded));
-            CK(s->d_scan_barrier.ensure(1));
-            CK(cudaMemsetAsync(s->d_scan_barrier.p, 0, sizeof(uint32_t), s->stream));
+            CK(s->d_scan_barrier.ensure(4));  // [0] k2_scan_fused*; [1..3] k2_scan_scatter_fused (scan, scatter, generation)
+            CK(cudaMemsetAsync(s->d_scan_barrier.p, 0, 4 * sizeof(uint32_t), s->stream));
             if (!s->scan_fused_capacity) {
                 int per_sm = 0, sms = 0;
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_fused, SCAN_THREADS, 0));
@@ -1016,6 +1019,30 @@ int Ops::launch_particle_links(const SubstepCtx &c, int phase, bool *ghosts_done
 int Ops::launch_grid_build(const SubstepCtx &c) {
     if (!c.discs) return BENDY_OK;
     cudaStream_t st = c.st;
+    if (s->sort_fused && s->scan_tiles_per_cta == 1) {
+        if (!s->sort_fused_capacity) {
+            int per_sm = 0, sms = 0;
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+            if (c.K)
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_scatter_fused<true>, SCAN_THREADS, 0));
+            else
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_scatter_fused<false>, SCAN_THREADS, 0));
+            s->sort_fused_capacity = (uint32_t)std::max(per_sm * sms, 1);
+        }
+        if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->sort_fused_capacity * 85) {
+            if (c.K)
+                LAUNCH(BENDY_K_GRID_BUILD,
+                       launch_k(c.pdl > 0, k2_scan_scatter_fused<true>, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
+                                s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p + 1, c.pos, s->nP, c.prm, s->n_cells,
+                                s->d_sorted_pos.p, s->d_slot_of.p, s->d_sorted_id.p));
+            else
+                LAUNCH(BENDY_K_GRID_BUILD,
+                       launch_k(c.pdl > 0, k2_scan_scatter_fused<false>, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
+                                s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p + 1, c.pos, s->nP, c.prm, s->n_cells,
+                                s->d_sorted_pos.p, s->d_slot_of.p, s->d_sorted_id.p));
+            return BENDY_OK;
+        }
+    }
     if (s->scan_tiles_per_cta == 2) {
         LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan_fused_mt<2>, s->n_scan_tiles / 2, SCAN_THREADS, 0, st,
                                             s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
@@ -1036,7 +1063,17 @@ int Ops::launch_grid_build(const SubstepCtx &c) {
     LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scatter<ID, AG>, cdiv(s->nP, 256), 256, 0, st, c.pos, s->nP, c.prm, \
                                         s->n_cells, s->d_cell_start.p, s->d_scan_barrier.p, s->d_sorted_pos.p,          \
                                         s->d_slot_of.p, s->d_sorted_id.p))
-    if (c.K && s->scatter_agg)
+    if (s->scatter_ilp) {
+        const uint32_t g4 = cdiv(s->nP, 256 * 4);
+        if (c.K)
+            LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scatter_ilp<true, 4>, g4, 256, 0, st, c.pos, s->nP, c.prm, s->n_cells,
+                                                s->d_cell_start.p, s->d_scan_barrier.p, s->d_sorted_pos.p, s->d_slot_of.p,
+                                                s->d_sorted_id.p));
+        else
+            LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scatter_ilp<false, 4>, g4, 256, 0, st, c.pos, s->nP, c.prm, s->n_cells,
+                                                s->d_cell_start.p, s->d_scan_barrier.p, s->d_sorted_pos.p, s->d_slot_of.p,
+                                                s->d_sorted_id.p));
+    } else if (c.K && s->scatter_agg)
         SCATTER(true, true);
     else if (c.K)
         SCATTER(true, false);
@@ -1325,6 +1362,8 @@ bendy_solver *bendy_create(int device) {
     if (const char *v = getenv("BENDY_SCAN_MT")) s->scan_mt = atoi(v) != 0;
     if (const char *v = getenv("BENDY_NARROW_DENSE")) s->narrow_dense = atoi(v) != 0;
     if (const char *v = getenv("BENDY_HALO_FUSED")) s->halo_fused = atoi(v) != 0;
+    if (const char *v = getenv("BENDY_SCATTER_ILP")) s->scatter_ilp = atoi(v) != 0;
+    if (const char *v = getenv("BENDY_SORT_FUSED")) s->sort_fused = atoi(v) != 0;
     if (const char *v = getenv("BENDY_PDL")) s->pdl = atoi(v);
     if (const char *v = getenv("BENDY_PDL_NCCL")) s->pdl_nccl = atoi(v) != 0;
     // BENDY_SIDE_PRIORITY=1: the circle / polygon branches get the highest stream priority, so their few
@@ -1988,6 +2027,7 @@ int bendy_get_stats(bendy_solver *s, uint64_t *out, int n) {
     for (int k = 0; k < n; k++) out[k] = 0;
     if (n > 4) out[4] = s->scan_tiles_per_cta;  // 2 / 4: k2_scan_fused_mt is in use (BENDY_SCAN_MT)
     if (n > 5) out[5] = (s->narrow_dense && !s->has_k) ? 1 : 0;
+    if (n > 6) out[6] = s->sort_fused_capacity;  // != 0: k2_scan_scatter_fused was considered (BENDY_SORT_FUSED)
     if (!s->d_flags.p) return BENDY_OK;
     if (int rc = ops.bind()) return rc;
     int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 OUT=gpurun_out/r2_ab.txt
 if [ "$1" = "strips" ]; then
   N=${2:-8}
-  for cfg in "" "BENDY_SCAN_MT=1" "BENDY_HALO_FUSED=1" "BENDY_PDL_NCCL=1" "BENDY_NARROW_DENSE=1" \
+  for cfg in "" "BENDY_SCAN_MT=1" "BENDY_HALO_FUSED=1" "BENDY_PDL_NCCL=1" "BENDY_NARROW_DENSE=1" "BENDY_SCATTER_ILP=1" \
              "BENDY_SCAN_MT=1 BENDY_HALO_FUSED=1 BENDY_PDL_NCCL=1" \
              "BENDY_SCAN_MT=1 BENDY_HALO_FUSED=1 BENDY_PDL_NCCL=1 BENDY_NARROW_DENSE=1"; do
     label=$(echo "strips${N}_${cfg:-default}" | tr ' =' '__')
@@ -31,11 +31,11 @@ BENDY_TEST_UNPROVEN=1 timeout 600 python -m pytest tests/test_z_gpu_variants.py 
 echo "variant tests exit code $?" | tee -a $OUT
 tail -3 gpurun_out/r2_variant_tests.log | tee -a $OUT
 # 2. C3 graph-mode substep time early / mid / late per switch
-for cfg in "" "BENDY_NARROW_DENSE=1"; do
+for cfg in "" "BENDY_NARROW_DENSE=1" "BENDY_SCATTER_ILP=1" "BENDY_SORT_FUSED=1" "BENDY_SORT_FUSED=1 BENDY_NARROW_DENSE=1"; do
   env $cfg timeout 200 python profiles/quick_c3.py "C3 ${cfg:-default}" | tee -a $OUT
 done
 # 3. the 2M-disc-per-rank strip problem of the 8-GPU run on ONE GPU (same kernels, no exchange partner): grid build
-for cfg in "" "BENDY_SCAN_MT=1" "BENDY_SCAN_MT=1 BENDY_NARROW_DENSE=1"; do
+for cfg in "" "BENDY_SCAN_MT=1" "BENDY_SCAN_MT=1 BENDY_SCATTER_ILP=1" "BENDY_SCAN_MT=1 BENDY_NARROW_DENSE=1"; do
   env $cfg timeout 300 python profiles/strip_rank_kernels.py "rank-of-8 ${cfg:-default}" | tee -a $OUT
 done
 # 4. compute-sanitizer on the variants (small scenes)

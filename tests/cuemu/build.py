@@ -31,6 +31,7 @@ _LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)\s*<<<(.+?)>>>\s*\(", re.S)
 _EXTERN_SHARED = re.compile(r"extern\s+__shared__\s+([\w ]+?)\s+(\w+)\s*\[\s*\]\s*;")
 _SHARED = re.compile(r"^(\s*)__shared__\s+((?:unsigned\s+|volatile\s+)*\w+)\s+([^;\n]+);", re.M)
 _ASM = re.compile(r'asm\s+volatile\s*\(\s*"griddepcontrol[^"]*"[^;]*;')
+_SPIN2 = re.compile(r"(while\s*\(\(int32_t\)\(\*\(volatile uint32_t \*\)word - target\) < 0\))\s*\{\s*\}")
 _SPIN = re.compile(r"while\s*\(\*\(volatile uint32_t \*\)barrier < gridDim\.x\)\s*\{\s*\}")
 
 
@@ -64,6 +65,8 @@ def transform(text: str, name: str) -> str:
     text, n_launch = _LAUNCH.subn(launch, text)
     text = _ASM.sub(";", text)
     text, n_spin = _SPIN.subn("while (*(volatile uint32_t *)barrier < gridDim.x) { cuemu::yield_spin(); }", text)
+    text, n_spin2 = _SPIN2.subn(r"\1 { cuemu::yield_spin(); }", text)
+    n_spin += n_spin2
     if any("<<<" in ln and not ln.lstrip().startswith("//") for ln in text.splitlines()):
         raise SystemExit(f"cuemu/build.py: an unconverted <<< >>> launch is left in {name}")
     if "__shared__" in text.replace("// ", ""):

@@ -175,3 +175,50 @@ def test_strip_variants_match_single_solver(switches):
     stats = grp.halo_stats()
     assert all(o == 0 and st == 0 for _, _, o, st in stats), stats
     assert sum(a + b for a, b, _, _ in stats) > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# BENDY_SCATTER_ILP=1: 4 discs per thread in the counting-sort scatter
+def test_scatter_with_four_discs_per_thread_matches_default():
+    sc = scenes.c2_free_particles(60, 40)
+    sc.bounds = (0.0, 0.0, 40.0, 16.0)
+    same_bits(run(sc, 120), run(sc, 120, BENDY_SCATTER_ILP=1))
+    sc3 = scenes.c3_softbody_field(4, 2, 6, 8)
+    sc3.bounds = (0.0, 0.0, 128.0, 64.0)
+    sc3.particles = (sc3.particles - np.array([40.0, 0.0], f32)).astype(f32)
+    same_bits(run(sc3, 80), run(sc3, 80, BENDY_SCATTER_ILP=1, BENDY_NARROW_DENSE=1))
+    # inverse masses need the sorted ids; a particle count that is not a multiple of the 1024 discs per CTA
+    rng = np.random.default_rng(3)
+    pts = (np.array([5.0, 5.0]) + rng.uniform(0.0, 6.0, size=(1531, 2))).astype(f32)
+    pts[11] = [np.nan, 1.0]
+    scc = scenes.Scene("crowd", (0.0, 0.0, 32.0, 32.0), particle_radius=0.1, particles=pts)
+    k = rng.choice(np.array([0.0, 0.5, 1.0, 2.0], f32), len(pts)).astype(f32)
+    a, b = run(scc, 0), run(scc, 0, BENDY_SCATTER_ILP=1)
+    for g in (a, b):
+        g.set_particle_inv_mass(k)
+        g.update(scc.dt, n=25)
+    same_bits(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# BENDY_SORT_FUSED=1: scan + scatter in one launch (second grid barrier, generation-counted barrier words)
+@pytest.mark.parametrize("width,height,cell,fits", [(40.0, 16.0, 0.24, True), (128.0, 64.0, 0.24, False)] if EMU else
+                         [(128.0, 128.0, 0.42, True), (2048.0, 2048.0, 0.42, False)])
+def test_fused_scan_scatter_matches_default(width, height, cell, fits):
+    sc = disc_scene(width, height)
+    n = 60 if EMU else 150
+    a = run(sc, n, grid_cell=cell)
+    b = run(sc, n, grid_cell=cell, BENDY_SORT_FUSED=1)
+    same_bits(a, b)
+    assert b.stats()["sort_fused_capacity"] > 0
+    ka, kb = a.schedule_info()["kernels_per_substep"], b.schedule_info()["kernels_per_substep"]
+    assert kb == (ka - 1 if fits else ka), (ka, kb)
+    # with inverse masses (sorted ids) and through many graph replays of a multi-substep update
+    sc2 = disc_scene(width, height)
+    sc2.sub_steps, sc2.dt = 4, float(f32(4 / 120.0))
+    k = np.where(np.arange(sc2.n_particles) % 7 == 0, 0.25, 1.0).astype(f32)
+    c, d = run(sc2, 0, grid_cell=cell), run(sc2, 0, grid_cell=cell, BENDY_SORT_FUSED=1, BENDY_NARROW_DENSE=1)
+    for g in (c, d):
+        g.set_particle_inv_mass(k)
+        g.update(sc2.dt, n=20)
+    same_bits(c, d)
