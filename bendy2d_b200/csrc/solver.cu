@@ -170,6 +170,7 @@ struct bendy_solver {
     DevBuf<uint32_t> d_scan_barrier;
     uint32_t scan_fused_capacity = 0;  // CTAs of k2_scan_fused that can be resident at once
     bool sort_fused = false;           // BENDY_SORT_FUSED=1: k2_scan_scatter_fused (scan + scatter in one launch)
+    bool sort_fused_force = false;     // BENDY_SORT_FUSED=2: skip the residency check (experiments; the barrier times out)
     uint32_t sort_fused_capacity = 0;
     bool scatter_ilp = false;          // BENDY_SCATTER_ILP=1: k2_scatter_ilp (4 discs per thread)
     bool halo_fused = false;           // BENDY_HALO_FUSED=1: send-buffer reset + ghost histogram in one launch
@@ -377,6 +378,12 @@ int Ops::check_flags() {
     CK(cudaStreamSynchronize(s->stream));
     if (f) {
         CK(cudaMemsetAsync(s->d_flags.p, 0, sizeof(int), s->stream));
+        if (f & FLAG_GRID_BARRIER_TIMEOUT) {
+            s->sticky = BENDY_ERR_CUDA;
+            return fail(BENDY_ERR_CUDA,
+                        "a software grid barrier (BENDY_SCAN_MT / BENDY_SORT_FUSED kernels) timed out: not every CTA of "
+                        "the grid was resident; the state of the solver is invalid");
+        }
         // Only the particle-polygon contact (ext) takes its candidates from the tile lists.  The reference's
         // polygon<->polygon pass is exact whatever the bins hold: the pair pre-scan answers an overflowing
         // tile or an unbinned polygon with "start at row 0" and the pass itself compares all boxes.
@@ -1029,26 +1036,26 @@ int Ops::launch_grid_build(const SubstepCtx &c) {
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_scatter_fused<false>, SCAN_THREADS, 0));
             s->sort_fused_capacity = (uint32_t)std::max(per_sm * sms, 1);
         }
-        if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->sort_fused_capacity * 85) {
+        if (s->sort_fused_force || (uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->sort_fused_capacity * 85) {
             if (c.K)
                 LAUNCH(BENDY_K_GRID_BUILD,
                        launch_k(c.pdl > 0, k2_scan_scatter_fused<true>, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
-                                s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p + 1, c.pos, s->nP, c.prm, s->n_cells,
+                                s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p + 1, s->d_flags.p, c.pos, s->nP, c.prm, s->n_cells,
                                 s->d_sorted_pos.p, s->d_slot_of.p, s->d_sorted_id.p));
             else
                 LAUNCH(BENDY_K_GRID_BUILD,
                        launch_k(c.pdl > 0, k2_scan_scatter_fused<false>, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
-                                s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p + 1, c.pos, s->nP, c.prm, s->n_cells,
+                                s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p + 1, s->d_flags.p, c.pos, s->nP, c.prm, s->n_cells,
                                 s->d_sorted_pos.p, s->d_slot_of.p, s->d_sorted_id.p));
             return BENDY_OK;
         }
     }
     if (s->scan_tiles_per_cta == 2) {
         LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan_fused_mt<2>, s->n_scan_tiles / 2, SCAN_THREADS, 0, st,
-                                            s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
+                                            s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p, s->d_flags.p));
     } else if (s->scan_tiles_per_cta == 4) {
         LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan_fused_mt<4>, s->n_scan_tiles / 4, SCAN_THREADS, 0, st,
-                                            s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
+                                            s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p, s->d_flags.p));
     } else if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->scan_fused_capacity * 85) {
         // every scan CTA fits on the device at once (15% spare; side-branch kernels finish on their own)
         LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan_fused, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
@@ -1363,7 +1370,7 @@ bendy_solver *bendy_create(int device) {
     if (const char *v = getenv("BENDY_NARROW_DENSE")) s->narrow_dense = atoi(v) != 0;
     if (const char *v = getenv("BENDY_HALO_FUSED")) s->halo_fused = atoi(v) != 0;
     if (const char *v = getenv("BENDY_SCATTER_ILP")) s->scatter_ilp = atoi(v) != 0;
-    if (const char *v = getenv("BENDY_SORT_FUSED")) s->sort_fused = atoi(v) != 0;
+    if (const char *v = getenv("BENDY_SORT_FUSED")) s->sort_fused = atoi(v) != 0, s->sort_fused_force = atoi(v) == 2;
     if (const char *v = getenv("BENDY_PDL")) s->pdl = atoi(v);
     if (const char *v = getenv("BENDY_PDL_NCCL")) s->pdl_nccl = atoi(v) != 0;
     // BENDY_SIDE_PRIORITY=1: the circle / polygon branches get the highest stream priority, so their few

@@ -31,7 +31,6 @@ _LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)\s*<<<(.+?)>>>\s*\(", re.S)
 _EXTERN_SHARED = re.compile(r"extern\s+__shared__\s+([\w ]+?)\s+(\w+)\s*\[\s*\]\s*;")
 _SHARED = re.compile(r"^(\s*)__shared__\s+((?:unsigned\s+|volatile\s+)*\w+)\s+([^;\n]+);", re.M)
 _ASM = re.compile(r'asm\s+volatile\s*\(\s*"griddepcontrol[^"]*"[^;]*;')
-_SPIN2 = re.compile(r"(while\s*\(\(int32_t\)\(\*\(volatile uint32_t \*\)word - target\) < 0\))\s*\{\s*\}")
 _SPIN = re.compile(r"while\s*\(\*\(volatile uint32_t \*\)barrier < gridDim\.x\)\s*\{\s*\}")
 
 
@@ -65,8 +64,7 @@ def transform(text: str, name: str) -> str:
     text, n_launch = _LAUNCH.subn(launch, text)
     text = _ASM.sub(";", text)
     text, n_spin = _SPIN.subn("while (*(volatile uint32_t *)barrier < gridDim.x) { cuemu::yield_spin(); }", text)
-    text, n_spin2 = _SPIN2.subn(r"\1 { cuemu::yield_spin(); }", text)
-    n_spin += n_spin2
+
     if any("<<<" in ln and not ln.lstrip().startswith("//") for ln in text.splitlines()):
         raise SystemExit(f"cuemu/build.py: an unconverted <<< >>> launch is left in {name}")
     if "__shared__" in text.replace("// ", ""):
@@ -99,7 +97,7 @@ def build(force: bool = False) -> str:
         open(os.path.join(gen, f if f != "solver.cu" else "solver_emu.cpp"), "w").write(text)
     cxx = os.environ.get("CXX", "g++")
     flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-fno-fast-math",
-             "-fno-strict-aliasing", "-I", os.path.join(HERE, "include")]
+             "-fno-strict-aliasing", "-DBENDY_SPIN_HOOK()=cuemu::yield_spin()", "-DBENDY_SPIN_LIMIT=150000000ll", "-I", os.path.join(HERE, "include")]
     cmd = [cxx] + flags + ["-o", LIB, os.path.join(gen, "solver_emu.cpp"), os.path.join(gen, "plan.cpp"),
                            os.path.join(HERE, "runtime.cpp"), "-ldl"]
     subprocess.check_call(cmd)

@@ -194,6 +194,8 @@ template <typename T>
 static inline T __ldcg(const T *p) {
     return *p;
 }
+long long cuemu_clock64();
+static inline long long clock64() { return cuemu_clock64(); }  // nanoseconds of the host's steady clock
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline void __syncthreads() { cuemu::sync_block(); }

@@ -73,6 +73,7 @@ constexpr size_t kStack = 256 * 1024;
 constexpr uint32_t kPool = 2048;  // fibers = the most CUDA threads resident at once (8 "SMs" x 256)
 constexpr int kMaxDynDefault = 48 * 1024, kMaxDynOptIn = 227 * 1024;
 
+uint64_t g_spins = 0;       // busy-wait iterations: not progress, but the spinner may give up on its own (timeout)
 std::recursive_mutex g_mu;  // one launch at a time, whichever OS thread it comes from
 void *g_sched_sp = nullptr;
 std::vector<Fiber *> g_pool;
@@ -165,8 +166,9 @@ void run_batch(std::vector<Cta> &ctas, uint32_t threads, size_t smem) {
             remaining++;
         }
     }
+    auto last_progress = std::chrono::steady_clock::now();
     while (true) {
-        const uint64_t ev0 = g.events;
+        const uint64_t ev0 = g.events, spins0 = g_spins;
         uint32_t alive = 0;
         for (Cta &c : ctas)
             for (Fiber *f : c.fibers) {
@@ -176,7 +178,12 @@ void run_batch(std::vector<Cta> &ctas, uint32_t threads, size_t smem) {
                 resume(f);
             }
         if (!alive) break;
-        if (g.events == ev0) die("deadlock: no thread made progress (mismatched barrier / warp primitive, or a grid barrier whose CTAs are not all resident)");
+        if (g.events != ev0) {
+            last_progress = std::chrono::steady_clock::now();
+        } else if (g_spins == spins0 || std::chrono::steady_clock::now() - last_progress > std::chrono::seconds(4)) {
+            // nobody moved and nobody is busy-waiting (or the busy-waiters never give up)
+            die("deadlock: no thread made progress (mismatched barrier / warp primitive, or a grid barrier whose CTAs are not all resident)");
+        }
     }
     (void)remaining;
 }
@@ -250,7 +257,10 @@ void sync_block() {
     while (f->at_barrier) to_scheduler();
 }
 
-void yield_spin() { to_scheduler(); }
+void yield_spin() {
+    g_spins++;
+    to_scheduler();
+}
 
 uint32_t warp_live() { return g.cur->cta->warps[g.cur->warp].live; }
 
@@ -306,6 +316,10 @@ void launch(const char *name, const void *fn_key, dim3 grid, dim3 block, size_t 
 }  // namespace cuemu
 
 using namespace cuemu;
+
+long long cuemu_clock64() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // host callback in stream order (recorded during capture, replayed with the graph): the NCCL stub's exchange
 extern "C" int cuemu_enqueue_host(void (*fn)(void *), void *arg) {

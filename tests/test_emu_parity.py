@@ -56,6 +56,21 @@ def test_emulator_primitives_self_check(emu_lib, tmp_path):
         assert r.returncode != 0 and msg in r.stderr, (mode, r.stdout, r.stderr)
 
 
+def test_grid_barrier_kernels_time_out_instead_of_hanging(emu_lib, tmp_path):
+    """kernel-level (tests/cuemu/kernel_unit.cpp): k2_scan_scatter_fused / k2_scan_fused_mt on a resident grid sort /
+    scan correctly; on a grid larger than the device their software barrier gives up, raises the flag and every
+    CTA leaves"""
+    build_dir = os.path.join(HERE, "cuemu", "_build")
+    exe = tmp_path / "kernel_unit"
+    subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-w", "-ffp-contract=off",
+                           "-DBENDY_SPIN_HOOK()=cuemu::yield_spin()", "-DBENDY_SPIN_LIMIT=150000000ll",
+                           "-I", os.path.join(HERE, "cuemu", "include"), "-I", os.path.join(build_dir, "bendy2d_b200", "csrc"),
+                           os.path.join(HERE, "cuemu", "kernel_unit.cpp"), os.path.join(HERE, "cuemu", "runtime.cpp"),
+                           "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "kernel_unit ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_parity_suite_on_emulator(emu_lib):
     out = run_gpu_tests_on_emulator(emu_lib, ["tests/test_gpu_parity.py", "-k", "not full_size"])
     assert "failed" not in out
