@@ -469,10 +469,14 @@ int Ops::rebuild() {
     s->nOwned = (uint32_t)s->p_pos.size();
     s->nP = s->nOwned + (s->halo_on ? 2 * s->ghost_cap : 0);  // disc slots = owned + ghosts
     s->nC = (uint32_t)s->c_pos.size();
-    if (s->halo_on && (s->nC || !s->polys.empty() || !s->p_k.empty()))
+    // Polygons are fine in a strip: they never receive anything from a particle (solver.rs:178-187 only pairs
+    // polygons with polygons; the particle-polygon extension only moves the particle), so every strip carries
+    // an identical copy that evolves identically.  Circles would need the particles' fixed-point corrections
+    // summed over all strips, inverse masses the neighbours' scales next to the ghost positions: not yet.
+    if (s->halo_on && (s->nC || !s->p_k.empty()))
         return fail(BENDY_ERR_UNSUPPORTED,
-                    "strips (halo exchange) support free particles and particle links only: no circles, polygons "
-                    "or inverse masses in a sharded solver yet");
+                    "strips (halo exchange) support free particles, particle links and polygons: no circles or inverse "
+                    "masses in a sharded solver yet");
     s->nG = (uint32_t)s->g_pos.size();
     s->N = s->nP + s->nC + s->nG;
     s->Npad = (s->N + 1u) & ~1u;

@@ -31,13 +31,22 @@ def _worker(rank, world, port, case, q):
 
     assert _lib.LIB_PATH.endswith("_emu.so")
     try:
-        if case == "bodies":
+        if case in ("bodies", "polygons"):
             sc = touching_field() if world < 4 else touching_field(16, 2)
+            if case == "polygons":
+                sc = touching_field(8, 2)  # two rows of bodies (y 8..23) above the obstacles  # replicated obstacles under the bodies, one dynamic overlapping pair
+                src = scenes.c3_softbody_field(2, 1, 0, 10)
+                placed = [(p - p.mean(0) + np.array([57.0 + 3.3 * j, 27.5])).astype(f32) for j, p in enumerate(src.polygons)]
+                placed[1] = (placed[0] + np.array([1.0, 0.5], f32)).astype(f32)
+                sc.polygons, sc.polygons_static = placed, [False, False] + [True] * (len(placed) - 2)
+                sc.polygon_contact = True
+                sc.bounds = (0.0, 0.0, 128.0, 64.0)
             sv = strips.StripSolver(sc, rank, world, 0, dist)
-            for _ in range(3):
+            rounds = 3 if case == "bodies" else 2  # later the bodies bounce off the obstacles past the stray margin
+            for _ in range(rounds):
                 sv.update(sc.dt, n=20)
                 sent = sv.check_halo()
-            n_updates, rebalanced = 60, 0
+            n_updates, rebalanced = 20 * rounds, 0
         else:  # free particles pile up and spread sideways: ownership has to follow (rebalance over the group)
             sc = scenes.c2_free_particles(80, 30)
             sc.bounds = (0.0, 0.0, 48.0, 12.0)
@@ -77,11 +86,19 @@ def _run(world, case, extra_env=None):
     try:
         ctx = mp.get_context("spawn")
         q = ctx.Queue()
-        port = 33500 + (os.getpid() % 2000) + 7 * world + (11 if case == "bodies" else 0)
+        port = 33500 + (os.getpid() % 2000) + 7 * world + {"bodies": 11, "polygons": 23}.get(case, 0)
         procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
         for p in procs:
             p.start()
-        res = [q.get(timeout=600) for _ in procs]
+        res = []
+        for _ in procs:
+            res.append(q.get(timeout=300))
+            if res[-1][1] is not True:  # a rank failed: its peers are stuck in the exchange, do not wait for them
+                for p in procs:
+                    p.join(timeout=2)
+                    if p.is_alive():
+                        p.kill()
+                raise AssertionError(f"rank {res[-1][0]} failed: {res[-1][2]}")
         for p in procs:
             p.join(timeout=120)
             assert p.exitcode == 0
@@ -107,3 +124,8 @@ def test_nccl_strip_solvers_rebalance_over_the_process_group():
     res = _run(3, "free")
     assert all(ok is True for _, ok, *_ in res), res
     assert res[0][3] > 0, "the scene never needed rebalancing: nothing was tested"
+
+
+def test_nccl_strip_solvers_with_replicated_polygons():
+    res = _run(2, "polygons")
+    assert all(ok is True for _, ok, *_ in res), res

@@ -42,10 +42,15 @@ def test_partition_invariants(world):
     assert len(np.unique(strips.body_ids(sc))) == len(np.unique(sc.body_of))
 
 
-def test_partition_rejects_circles():
+def test_partition_rejects_circles_and_replicates_polygons():
     sc = scenes.c3_softbody_field(2, 1, 2, 0)
     with pytest.raises(ValueError):
         strips.partition_scene(sc, 2)
+    sc = scenes.c3_softbody_field(4, 1, 0, 5)
+    parts = strips.partition_scene(sc, 2)
+    for p in parts:
+        assert len(p.scene.polygons) == 5 and p.scene.polygons_static == sc.polygons_static
+        assert p.scene.polygon_contact == sc.polygon_contact
 
 
 def _halo_worker(rank, world, port, q):
