@@ -34,6 +34,12 @@ def run_gpu_tests_on_emulator(emu_lib, args, timeout=900, extra_env=None):
     env.update({"BENDY2D_B200_LIB": emu_lib, "BENDY_CUDA_EMU": "1"})
     env.update(extra_env or {})
     cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"] + args
+    try:  # the emulated suites are CPU-bound and independent: spread them over a few cores when xdist is there
+        import xdist  # noqa: F401
+
+        cmd += ["-n", str(max(1, min(4, (os.cpu_count() or 2) // 2)))]
+    except ImportError:
+        pass
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-40:])
     assert r.returncode == 0, f"emulated run failed ({' '.join(args)}):\n{tail}"
