@@ -71,6 +71,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -100,6 +101,7 @@ struct NcclApi {
         NCCL_SYM(CommDestroy, "ncclCommDestroy")
         NCCL_SYM(Send, "ncclSend")
         NCCL_SYM(Recv, "ncclRecv")
+        NCCL_SYM(AllReduce, "ncclAllReduce")
         NCCL_SYM(GroupStart, "ncclGroupStart")
         NCCL_SYM(GroupEnd, "ncclGroupEnd")
         NCCL_SYM(GetErrorString, "ncclGetErrorString")
@@ -109,7 +111,7 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
-enum Phase { PHASE_ALL = 0, PHASE_A = 1, PHASE_B = 2 };
+enum Phase { PHASE_ALL = 0, PHASE_A = 1, PHASE_B = 2, PHASE_C = 3 };
 
 struct PendingEvent {
     int cls;
@@ -306,7 +308,8 @@ struct Ops {  // helper with access to the solver; keeps bendy_solver a plain st
     int launch_halo_receive(const SubstepCtx &c, cudaStream_t q_clear);
     int launch_particle_links(const SubstepCtx &c, int phase, bool *ghosts_done);
     int launch_grid_build(const SubstepCtx &c);
-    int launch_collide_integrate_discs(const SubstepCtx &c);
+    int launch_collide_integrate_discs(const SubstepCtx &c, int phase);
+    int launch_circle_tail(const SubstepCtx &c);
     int launch_collide_integrate_plain(const SubstepCtx &c);
     int build_graph(uint32_t substeps);
     void drop_graph();
@@ -471,12 +474,17 @@ int Ops::rebuild() {
     s->nC = (uint32_t)s->c_pos.size();
     // Polygons are fine in a strip: they never receive anything from a particle (solver.rs:178-187 only pairs
     // polygons with polygons; the particle-polygon extension only moves the particle), so every strip carries
-    // an identical copy that evolves identically.  Circles would need the particles' fixed-point corrections
-    // summed over all strips, inverse masses the neighbours' scales next to the ghost positions: not yet.
-    if (s->halo_on && (s->nC || !s->p_k.empty()))
+    // an identical copy that evolves identically.  Circles are replicated as well: every strip runs the same
+    // circle links and circle-circle pass, and the fixed-point corrections its OWN discs collected for each
+    // Circle are summed over all strips (an integer all-reduce, hence order-free and bit-identical to the
+    // unsharded sum) before the circles' tail applies them.  Inverse masses would need the neighbours' scales
+    // next to the ghost positions: not yet.
+    if (s->halo_on && !s->p_k.empty())
         return fail(BENDY_ERR_UNSUPPORTED,
-                    "strips (halo exchange) support free particles, particle links and polygons: no circles or inverse "
+                    "strips (halo exchange) support free particles, particle links, circles and polygons: no inverse "
                     "masses in a sharded solver yet");
+    if (s->halo_on && !s->c_k.empty())
+        return fail(BENDY_ERR_UNSUPPORTED, "strips (halo exchange): no inverse masses in a sharded solver yet");
     s->nG = (uint32_t)s->g_pos.size();
     s->N = s->nP + s->nC + s->nG;
     s->Npad = (s->N + 1u) & ~1u;
@@ -1008,7 +1016,7 @@ int Ops::launch_particle_links(const SubstepCtx &c, int phase, bool *ghosts_done
     // the interior partitions are relaxed.  Measured on 8 x B200 (C5, 2M discs per rank) the split
     // costs more than the exchange it hides (166 vs 153 us per substep), hence off by default.
     const bool overlap = s->halo_overlap && c.halo && phase == PHASE_ALL && c.branch && c.fuse_count && s->nccl_comm &&
-                         nb > 0 && nb < n_parts;
+                         nb > 0 && nb < n_parts && s->nC == 0;  // side[0] carries the circle chain when there are circles
     if (overlap) {
         cudaStream_t qx = s->side[0];  // free in strip mode (no circles)
         if (int rc = launch_links_local(c, c.st, 0, nb, 1)) return rc;
@@ -1099,8 +1107,9 @@ int Ops::launch_grid_build(const SubstepCtx &c) {
 // disc grid on: narrowphase + polygon contact + bounds + integrate for the free particles in one
 // launch; then the tails (circles: apply + bounds + integrate; polygon points: bounds + integrate),
 // each behind the narrowphase on its own branch
-int Ops::launch_collide_integrate_discs(const SubstepCtx &c) {
+int Ops::launch_collide_integrate_discs(const SubstepCtx &c, int phase) {
     cudaStream_t st = c.st;
+    if (phase == PHASE_C) return launch_circle_tail(c);  // same-process strips: the corrections were summed by the group
     K2Args a{c.pos,    s->d_prev.p, c.dk,  s->d_slot_of.p, s->d_sorted_id.p,       s->d_sorted_pos.p,    s->d_cell_start.p, s->n_cells,
              s->nP,    s->nOwned,   s->nC, s->d_crad.p,    s->d_circ_tile_count.p, s->d_circ_tile_ids.p, s->d_circ_acc.p,
              s->d_circ_snap.p};
@@ -1122,8 +1131,41 @@ int Ops::launch_collide_integrate_discs(const SubstepCtx &c) {
         NARROW(false, false);
 #undef NARROW
     if (c.branch && (c.qc != st || c.qg != st)) CK(cudaEventRecord(s->ev_main, st));
-    if (s->nC) {
+    if (s->nC && !(phase == PHASE_B && c.halo)) {
         if (c.qc != st) CK(cudaStreamWaitEvent(c.qc, s->ev_main, 0));
+        if (c.halo && s->nccl_comm) {
+            // strips: the Circles are replicated; sum the corrections every strip's own discs collected for them
+            ncclResult_t r = g_nccl.AllReduce(s->d_circ_acc.p, s->d_circ_acc.p, 2 * (size_t)s->nC, ncclUint64, ncclSum,
+                                              s->nccl_comm, c.qc);
+            if (r != ncclSuccess) {
+                s->sticky = BENDY_ERR_CUDA;
+                return fail(BENDY_ERR_CUDA, std::string("NCCL error in ncclAllReduce: ") + g_nccl.GetErrorString(r));
+            }
+            if (s->capturing)
+                s->count_in_capture++;
+            else
+                s->launches++, s->k_launches[BENDY_K_HALO]++;
+        }
+        if (int rc = launch_circle_tail(c)) return rc;
+    }
+    if (s->nG) {
+        if (c.qg != st) CK(cudaStreamWaitEvent(c.qg, s->ev_main, 0));
+        const uint32_t first = s->nP + s->nC, n = s->nG, blocks_g = cdiv(n, 256);
+        if (c.acc && c.K)
+            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<true, true>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
+        else if (c.acc)
+            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<true, false>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
+        else if (c.K)
+            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<false, true>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
+        else
+            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<false, false>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
+    }
+    return BENDY_OK;
+}
+
+// tail of the substep for the Circles: apply the particles' corrections, bounds, integrate
+int Ops::launch_circle_tail(const SubstepCtx &c) {
+    {
         const uint32_t blocks_c = cdiv(s->nC, 128);
 #define CTAIL(A, KK)                                                                                            \
     LAUNCH(BENDY_K_CIRCLES, launch_k(c.pdl > 2, k_circle_tail<A, KK, true>, blocks_c, 128, 0, c.qc, c.k1,           \
@@ -1137,18 +1179,6 @@ int Ops::launch_collide_integrate_discs(const SubstepCtx &c) {
         else
             CTAIL(false, false);
 #undef CTAIL
-    }
-    if (s->nG) {
-        if (c.qg != st) CK(cudaStreamWaitEvent(c.qg, s->ev_main, 0));
-        const uint32_t first = s->nP + s->nC, n = s->nG, blocks_g = cdiv(n, 256);
-        if (c.acc && c.K)
-            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<true, true>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
-        else if (c.acc)
-            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<true, false>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
-        else if (c.K)
-            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<false, true>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
-        else
-            LAUNCH(BENDY_K_INTEGRATE, launch_k(c.pdl > 2, k1_integrate_range<false, false>, blocks_g, 256, 0, c.qg, c.k1, first, n, c.prm));
     }
     return BENDY_OK;
 }
@@ -1187,6 +1217,7 @@ int Ops::launch_collide_integrate_plain(const SubstepCtx &c) {
 int Ops::launch_substep(int phase) {
     SubstepCtx c = make_ctx();
     bool ghosts_done = false;
+    if (phase == PHASE_C) return (c.discs && c.halo && s->nC) ? launch_collide_integrate_discs(c, PHASE_C) : BENDY_OK;
     if (phase != PHASE_B) {
         if (int rc = launch_polygon_chain(c)) return rc;
         if (int rc = launch_circle_chain(c)) return rc;
@@ -1212,7 +1243,7 @@ int Ops::launch_substep(int phase) {
             CK(cudaStreamWaitEvent(c.st, s->ev_join[1], 0));
         }
     }
-    return c.discs ? launch_collide_integrate_discs(c) : launch_collide_integrate_plain(c);
+    return c.discs ? launch_collide_integrate_discs(c, phase) : launch_collide_integrate_plain(c);
 }
 
 int Ops::build_graph(uint32_t substeps) {
@@ -2218,6 +2249,43 @@ int bendy_update_group(bendy_solver **group, int n, uint32_t n_updates, float dt
             for (int side = 0; side < 2; side++)
                 if (s->peer[side]) CK(cudaStreamWaitEvent(s->stream, s->peer[side]->ev_xchg, 0));
             if (int rc = ops.launch_substep(PHASE_B)) return rc;
+        }
+        // replicated Circles: every strip's own discs collected fixed-point corrections for them; sum them over
+        // the group (integers: any order gives the same bits), hand every strip the total, then run the tails
+        if (group[0]->nC && group[0]->halo_on && group[0]->particle_radius > 0.f && group[0]->nP) {
+            bendy_solver *s0 = group[0];
+            const uint32_t n_acc = 2 * s0->nC;
+            for (int k = 0; k < n; k++) {
+                if (group[k]->nC != s0->nC) {
+                    g_last_error = s0->err = "group members need the same (replicated) circles";
+                    return BENDY_ERR_ARG;
+                }
+                bendy_solver *s = group[k];
+                OPS;
+                CK(cudaStreamSynchronize(s->stream));
+            }
+            {
+                bendy_solver *s = s0;
+                OPS;
+                if (int rc = ops.bind()) return rc;
+                for (int k = 1; k < n; k++) {
+                    k_acc_add<<<cdiv(n_acc, 128), 128, 0, s0->stream>>>(s0->d_circ_acc.p, group[k]->d_circ_acc.p, n_acc);
+                    CK(cudaGetLastError());
+                }
+                for (int k = 1; k < n; k++)
+                    CK(cudaMemcpyAsync(group[k]->d_circ_acc.p, s0->d_circ_acc.p, n_acc * sizeof(unsigned long long),
+                                       cudaMemcpyDeviceToDevice, s0->stream));
+                CK(cudaStreamSynchronize(s0->stream));
+            }
+            for (int k = 0; k < n; k++) {
+                bendy_solver *s = group[k];
+                OPS;
+                if (int rc = ops.bind()) return rc;
+                if (int rc = ops.launch_substep(PHASE_C)) return rc;
+            }
+        }
+        for (int k = 0; k < n; k++) {
+            bendy_solver *s = group[k];
             s->accel_pending = false;
             s->host_valid = false;
         }

@@ -78,11 +78,11 @@ class StripPart:
 
 def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodies: Optional[np.ndarray] = None,
                     cap_factor: float = 2.0) -> List[StripPart]:
-    """Split `scene` into `world` strips.  Polygons are replicated: every strip carries all of them (nothing a
-    particle does reaches a polygon, so the copies evolve identically).  Circles are not sharded yet (their
-    particle contacts would have to be summed over all strips): they must be absent."""
-    if len(scene.circles_r):
-        raise ValueError("strip sharding supports free particles, links and (replicated) polygons: no circles")
+    """Split `scene` into `world` strips.  Polygons and Circles are replicated: every strip carries all of them.
+    Nothing a particle does reaches a polygon, so the copies evolve identically; the corrections a strip's own
+    discs collect for a Circle are summed over all strips by the library (integer all-reduce) before they are
+    applied, so the Circles' copies stay identical too."""
+
     n = scene.n_particles
     if bodies is None:
         bodies = scene.body_of if scene.body_of is not None else body_ids(scene)
@@ -300,8 +300,8 @@ class StripSolver(_StripBase):
         """Re-partition by the CURRENT positions: every rank gathers the full state (rare, host side),
         cuts new strips of equal body count and rebuilds its local solver; pos and prev travel
         bit-exactly, so the trajectory is unchanged."""
-        if self.full_scene.polygons:
-            raise NotImplementedError("rebalance() does not carry the state of replicated polygons over yet")
+        if self.full_scene.polygons or len(self.full_scene.circles_r):
+            raise NotImplementedError("rebalance() does not carry the state of replicated polygons / circles over yet")
         pos, prev = self.solver.read_particles()
         gpos, gprev = gather_global_state(self.dist, self.world, self.device_index, self.part.global_index, pos, prev,
                                           self.full_scene.n_particles)
@@ -355,8 +355,8 @@ class LocalStripGroup:
         return any(st for _, _, _, st in self.halo_stats())
 
     def rebalance(self):
-        if self.scene.polygons:
-            raise NotImplementedError("rebalance() does not carry the state of replicated polygons over yet")
+        if self.scene.polygons or len(self.scene.circles_r):
+            raise NotImplementedError("rebalance() does not carry the state of replicated polygons / circles over yet")
         pos, prev = self.read_particles()
         g, b = self.solvers[0].gravity, self.solvers[0].bounds
         self.solvers = []

@@ -201,11 +201,14 @@ int bendy_set_grid_window(bendy_solver *s, float x0, float x1);
 /* rank 0 creates the NCCL id (128 bytes); the host layer (torch.distributed) broadcasts it */
 int bendy_nccl_unique_id(void *out128);
 /* joins the strip communicator: neighbours are rank-1 and rank+1; send/recv run on the solver's stream
- * inside the captured substep graph */
+ * inside the captured substep graph.  Circles and polygons are replicated on every strip; the fixed-point
+ * corrections a strip's own discs collect for the Circles are all-reduced (ncclUint64 sum) over the
+ * communicator before they are applied, so every copy stays identical to the unsharded run. */
 int bendy_halo_comm_nccl(bendy_solver *s, const void *unique_id128, int rank, int world);
 /* same-process transport between two neighbouring strips (1-GPU emulation, tests) */
 int bendy_halo_connect_local(bendy_solver *left, bendy_solver *right);
-/* lock-step update of several same-process strips (phase A | halo copy | phase B per substep) */
+/* lock-step update of several same-process strips (phase A | halo copy | phase B | sum of the Circles'
+ * corrections over the group | the Circles' tail, per substep) */
 int bendy_update_group(bendy_solver **group, int n, uint32_t n_updates, float dt, float gx, float gy, float bx,
                        float by, float bw, float bh);
 /* discs packed for each neighbour in the last substep; overflow != 0 means ghost_cap was too small;

@@ -3,7 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 typedef enum { ncclSuccess = 0, ncclUnhandledCudaError = 1, ncclSystemError = 2, ncclInternalError = 3 } ncclResult_t;
-typedef enum { ncclInt8 = 0, ncclFloat32 = 7, ncclFloat = 7 } ncclDataType_t;
+typedef enum { ncclInt8 = 0, ncclInt64 = 4, ncclUint64 = 5, ncclFloat32 = 7, ncclFloat = 7 } ncclDataType_t;
+typedef enum { ncclSum = 0 } ncclRedOp_t;
 typedef struct ncclComm *ncclComm_t;
 typedef struct {
     char internal[128];

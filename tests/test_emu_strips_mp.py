@@ -31,7 +31,7 @@ def _worker(rank, world, port, case, q):
 
     assert _lib.LIB_PATH.endswith("_emu.so")
     try:
-        if case in ("bodies", "polygons"):
+        if case in ("bodies", "polygons", "circles"):
             sc = touching_field() if world < 4 else touching_field(16, 2)
             if case == "polygons":
                 sc = touching_field(8, 2)  # two rows of bodies (y 8..23) above the obstacles  # replicated obstacles under the bodies, one dynamic overlapping pair
@@ -41,6 +41,12 @@ def _worker(rank, world, port, case, q):
                 sc.polygons, sc.polygons_static = placed, [False, False] + [True] * (len(placed) - 2)
                 sc.polygon_contact = True
                 sc.bounds = (0.0, 0.0, 128.0, 64.0)
+            if case == "circles":  # replicated Circles under the bodies: their corrections are all-reduced
+                sc = touching_field(8, 2)
+                sc.bounds = (0.0, 0.0, 128.0, 64.0)
+                sc.circles_pos = np.stack([57.0 + 3.9 * np.arange(10), np.full(10, 26.0)], 1).astype(f32)
+                sc.circles_pos[3] = sc.circles_pos[2] + np.array([0.8, 0.3], f32)
+                sc.circles_r = np.array([1.2, 0.9, 1.1, 1.0, 1.4, 0.8, 1.3, 1.0, 0.7, 1.2], f32)
             sv = strips.StripSolver(sc, rank, world, 0, dist)
             rounds = 3 if case == "bodies" else 2  # later the bodies bounce off the obstacles past the stray margin
             for _ in range(rounds):
@@ -60,12 +66,17 @@ def _worker(rank, world, port, case, q):
         pos, prev = sv.read_particles()
         gpos, gprev = strips.gather_global_state(dist, world, 0, sv.part.global_index, pos, prev, sc.n_particles)
         ok = True
-        if rank == 0:
+        if rank == 0 or case == "circles":
             ref = Solver()
             sc.load_into(ref)
             ref.update(sc.dt, n=n_updates)
             rp, rq = ref.read_particles()
             ok = np.array_equal(gpos.view(np.uint32), rp.view(np.uint32)) and np.array_equal(gprev.view(np.uint32), rq.view(np.uint32))
+            if case == "circles":  # every rank's copy of the Circles equals the unsharded ones
+                a, b = sv.read_circles(), ref.read_circles()
+                ok = ok and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+                moved = not np.array_equal(b[0][:, 0], sc.circles_pos[:, 0])  # the discs pushed them sideways
+                ok = ok and moved
         q.put((rank, ok, int(sum(sent)), rebalanced, sv.schedule_info()["kernels_per_substep"]))
     except Exception as e:  # report instead of hanging the other ranks' queue reader
         q.put((rank, False, repr(e), 0, 0))
@@ -86,7 +97,7 @@ def _run(world, case, extra_env=None):
     try:
         ctx = mp.get_context("spawn")
         q = ctx.Queue()
-        port = 33500 + (os.getpid() % 2000) + 7 * world + {"bodies": 11, "polygons": 23}.get(case, 0)
+        port = 33500 + (os.getpid() % 2000) + 7 * world + {"bodies": 11, "polygons": 23, "circles": 37}.get(case, 0)
         procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
         for p in procs:
             p.start()
@@ -128,4 +139,10 @@ def test_nccl_strip_solvers_rebalance_over_the_process_group():
 
 def test_nccl_strip_solvers_with_replicated_polygons():
     res = _run(2, "polygons")
+    assert all(ok is True for _, ok, *_ in res), res
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_nccl_strip_solvers_with_replicated_circles_all_reduce_their_corrections(world):
+    res = _run(world, "circles")
     assert all(ok is True for _, ok, *_ in res), res

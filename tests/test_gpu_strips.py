@@ -179,3 +179,39 @@ def test_strips_with_replicated_polygons_match_single_solver():
     sc2.load_into(free)
     free.update(sc.dt, n=20 * checked)
     assert not np.array_equal(bits(free.read_particles()[0]), bits(rp))
+
+
+def test_strips_with_replicated_circles_match_single_solver():
+    """Circles are replicated; the fixed-point corrections each strip's own discs collect for a Circle are summed
+    over the strips before the Circles' tail applies them (integer sums: same bits as the unsharded sum).  Bodies
+    fall onto a row of Circles (two of them linked, two overlapping) across 3 strips."""
+    sc = scenes.c3_softbody_field(8, 2, 0, 0)
+    col = (np.arange(sc.n_particles) // 500) % 8
+    sc.particles[:, 0] -= (col * 3.1).astype(f32)
+    sc.bounds = (0.0, 0.0, 128.0, 64.0)
+    sc.circles_pos = np.stack([57.0 + 3.9 * np.arange(10), np.full(10, 26.0)], 1).astype(f32)
+    sc.circles_pos[3] = sc.circles_pos[2] + np.array([0.8, 0.3], f32)  # an overlapping pair: the exact circle pass runs
+    sc.circles_r = np.array([1.2, 0.9, 1.1, 1.0, 1.4, 0.8, 1.3, 1.0, 0.7, 1.2], f32)
+    ref = Solver()
+    sc.load_into(ref)
+    grp = strips.LocalStripGroup(sc, 3)
+    checked = 0
+    for k in range(5):
+        ref.update(sc.dt, n=20)
+        grp.update(sc.dt, n=20)
+        if any(o or st for _, _, o, st in grp.halo_stats()):
+            break
+        rp, rq = ref.read_particles()
+        gp, gq = grp.read_particles()
+        assert max_ulp(gp, rp) == 0 and max_ulp(gq, rq) == 0, f"after {20 * (k + 1)} substeps"
+        rc = ref.read_circles()
+        for sv in grp.solvers:
+            gc = sv.read_circles()
+            assert max_ulp(gc[0], rc[0]) == 0 and max_ulp(gc[1], rc[1]) == 0, k
+        checked = k + 1
+    assert checked >= 3, "the halo went stale before the bodies had pushed the circles around"
+    still = Solver()  # the particles really pushed the Circles: alone they would be somewhere else
+    still.add_circles(sc.circles_pos, sc.circles_r)
+    still.bounds.size[:] = (128.0, 64.0)
+    still.update(sc.dt, n=20 * checked)
+    assert not np.array_equal(bits(still.read_circles()[0]), bits(rc[0]))

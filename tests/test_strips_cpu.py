@@ -42,15 +42,13 @@ def test_partition_invariants(world):
     assert len(np.unique(strips.body_ids(sc))) == len(np.unique(sc.body_of))
 
 
-def test_partition_rejects_circles_and_replicates_polygons():
-    sc = scenes.c3_softbody_field(2, 1, 2, 0)
-    with pytest.raises(ValueError):
-        strips.partition_scene(sc, 2)
-    sc = scenes.c3_softbody_field(4, 1, 0, 5)
+def test_partition_replicates_circles_and_polygons():
+    sc = scenes.c3_softbody_field(4, 1, 3, 5)
     parts = strips.partition_scene(sc, 2)
     for p in parts:
         assert len(p.scene.polygons) == 5 and p.scene.polygons_static == sc.polygons_static
         assert p.scene.polygon_contact == sc.polygon_contact
+        assert np.array_equal(p.scene.circles_pos, sc.circles_pos) and np.array_equal(p.scene.circles_r, sc.circles_r)
 
 
 def _halo_worker(rank, world, port, q):
