@@ -90,7 +90,7 @@ def test_parity_suite_on_emulator_plain_launches(emu_lib):
 
 def test_limits_strips_snapshot_golden_on_emulator(emu_lib):
     run_gpu_tests_on_emulator(emu_lib, ["tests/test_gpu_limits.py", "tests/test_gpu_strips.py", "tests/test_snapshot.py",
-                                        "tests/test_golden.py", "-k", "not 4200 and not nccl"])
+                                        "tests/test_golden.py", "tests/test_z_gpu_strips_replicated.py", "-k", "not 4200 and not nccl"])
 
 
 def test_opt_in_variants_on_emulator(emu_lib):
