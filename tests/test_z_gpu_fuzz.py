@@ -438,6 +438,19 @@ def test_random_strip_field_is_bit_identical_to_single_solver(seed):
     sc = scenes.Scene(f"strip fuzz {seed}", (0.0, 0.0, W, 24.0), particle_radius=0.1,
                       particles=np.concatenate(pts).astype(f32), links_ab=np.concatenate(ab).astype(np.uint32),
                       links_len=np.concatenate(ln).astype(f32), body_of=np.concatenate(body))
+    # replicated circles (their particle corrections are all-reduced over the strips) and polygons
+    replicated = False
+    if rng.uniform() < 0.5:
+        nc = int(rng.integers(1, 12))
+        sc.circles_pos = np.stack([rng.uniform(2, W - 2, nc), rng.uniform(12, 20, nc)], 1).astype(f32)
+        sc.circles_r = rng.uniform(0.3, 1.5, nc).astype(f32)
+        replicated = True
+    if rng.uniform() < 0.5:
+        ng = int(rng.integers(1, 6))
+        sc.polygons = [convex_ngon(rng, rng.uniform(4, W - 4), rng.uniform(14, 20)) for _ in range(ng)]
+        sc.polygons_static = [bool(rng.uniform() < 0.6) for _ in range(ng)]
+        sc.polygon_contact = any(sc.polygons_static) and bool(rng.uniform() < 0.7)
+        replicated = True
     sub = int(rng.choice([1, 2, 4]))
     sc.sub_steps, sc.dt = sub, float(f32(sub / 120.0))
     n_strips = int(rng.integers(2, 7))
@@ -468,6 +481,8 @@ def test_random_strip_field_is_bit_identical_to_single_solver(seed):
             pytest.skip(f"a disc moved {moved:.2f} between two polls: outside the rebalance contract (band {band:.2f})")
         before = after
         if grp.needs_rebalance():
+            if replicated:
+                pytest.skip("rebalance() does not carry circle / polygon state yet")
             try:
                 grp.rebalance()
             except ValueError as e:
@@ -478,3 +493,10 @@ def test_random_strip_field_is_bit_identical_to_single_solver(seed):
     gp, gq = grp.read_particles()
     rp, rq = ref.read_particles()
     assert max_ulp(gp, rp) == 0 and max_ulp(gq, rq) == 0, (seed, n_strips, n_bodies, rebalanced)
+    for sv in grp.solvers:  # every strip's copy of the replicated bodies equals the unsharded one
+        if len(sc.circles_r):
+            a, b = sv.read_circles(), ref.read_circles()
+            assert max_ulp(a[0], b[0]) == 0 and max_ulp(a[1], b[1]) == 0, (seed, "circles")
+        for j in range(len(sc.polygons)):
+            a, b = sv.read_polygon(j), ref.read_polygon(j)
+            assert max_ulp(a[0], b[0]) == 0 and max_ulp(a[1], b[1]) == 0 and max_ulp(a[2], b[2]) == 0, (seed, "polygon", j)
