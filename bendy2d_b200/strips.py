@@ -158,9 +158,36 @@ def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodi
     return parts
 
 
-def _load_part(part: StripPart, device: int) -> Solver:
+def replicated_state(sv: Solver):
+    """The state of the replicated bodies (Circles, polygons) of a strip solver, exactly as it is now: what
+    rebalance() hands to the re-partitioned solvers so that they carry on bit for bit."""
+    circles = sv.read_circles() if sv.get_circles_len() else None  # pos, prev, radius
+    polys = []
+    for k in range(sv.get_polygons_len()):
+        pos, prev, cen, st = sv.read_polygon(k)
+        nl = sv._L.bendy_polygon_link_len(sv._h, k)
+        ab, ln = np.empty((nl, 2), np.uint32), np.empty(nl, f32)
+        if nl:
+            sv._ck(sv._L.bendy_read_polygon_links(sv._h, k, ab.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                  ln.ctypes.data_as(C.POINTER(C.c_float))))
+        polys.append((pos, prev, cen, st, ab, ln))
+    return circles, polys
+
+
+def _load_part(part: StripPart, device: int, replicated=None) -> Solver:
+    """`replicated` (from replicated_state) replaces the scene's initial Circles / polygons by their current state"""
     sv = Solver(device)
-    part.scene.load_into(sv)
+    if replicated is None:
+        part.scene.load_into(sv)
+    else:
+        replace(part.scene, circles_pos=np.zeros((0, 2), f32), circles_r=np.zeros((0,), f32), polygons=[],
+                polygons_static=[]).load_into(sv)
+        circles, polys = replicated
+        if circles is not None:
+            sv.add_circles(circles[0], circles[2], prev_xy=circles[1])
+        for pos, prev, cen, st, ab, ln in polys:
+            sv.add_polygon_raw(pos, ab, ln, st, cen, prev_xy=prev)
+        sv.set_polygon_contact(part.scene.polygon_contact)
     if part.world > 1:
         sv._ck(sv._L.bendy_halo_configure(sv._h, part.ghost_cap, part.send_left_below, part.send_right_above,
                                           part.stray_left, part.stray_right))
@@ -249,12 +276,12 @@ class StripSolver(_StripBase):
         self._uid = None
         self._build(scene, None)
 
-    def _build(self, scene: Scene, prev: Optional[np.ndarray]):
+    def _build(self, scene: Scene, prev: Optional[np.ndarray], replicated=None):
         import torch
 
         rank, world, dist, device = self.rank, self.world, self.dist, self.device_index
         self.part = partition_scene(scene, world, self.band, self.bodies)[rank]
-        self.solver = _load_part(self.part, device)
+        self.solver = _load_part(self.part, device, replicated)
         if prev is not None:
             self.solver.write_particles(prev_xy=prev[self.part.global_index])
         if world > 1:
@@ -300,13 +327,13 @@ class StripSolver(_StripBase):
         """Re-partition by the CURRENT positions: every rank gathers the full state (rare, host side),
         cuts new strips of equal body count and rebuilds its local solver; pos and prev travel
         bit-exactly, so the trajectory is unchanged."""
-        if self.full_scene.polygons or len(self.full_scene.circles_r):
-            raise NotImplementedError("rebalance() does not carry the state of replicated polygons / circles over yet")
         pos, prev = self.solver.read_particles()
         gpos, gprev = gather_global_state(self.dist, self.world, self.device_index, self.part.global_index, pos, prev,
                                           self.full_scene.n_particles)
+        # the replicated Circles / polygons are identical on every rank: each keeps its own copy's state
+        rep = replicated_state(self.solver) if (self.full_scene.polygons or len(self.full_scene.circles_r)) else None
         self.solver = None
-        self._build(replace(self.full_scene, particles=gpos), gprev)
+        self._build(replace(self.full_scene, particles=gpos), gprev, rep)
 
 
 class LocalStripGroup:
@@ -319,9 +346,9 @@ class LocalStripGroup:
         self.bodies = bodies if bodies is not None else scene.body_of
         self._build(scene, None)
 
-    def _build(self, scene: Scene, prev: Optional[np.ndarray]):
+    def _build(self, scene: Scene, prev: Optional[np.ndarray], replicated=None):
         self.parts = partition_scene(scene, self.n_strips, self.band, self.bodies)
-        self.solvers = [_load_part(p, self.device) for p in self.parts]
+        self.solvers = [_load_part(p, self.device, replicated) for p in self.parts]
         if prev is not None:
             for p, s in zip(self.parts, self.solvers):
                 s.write_particles(prev_xy=prev[p.global_index])
@@ -355,9 +382,7 @@ class LocalStripGroup:
         return any(st for _, _, _, st in self.halo_stats())
 
     def rebalance(self):
-        if self.scene.polygons or len(self.scene.circles_r):
-            raise NotImplementedError("rebalance() does not carry the state of replicated polygons / circles over yet")
         pos, prev = self.read_particles()
-        g, b = self.solvers[0].gravity, self.solvers[0].bounds
+        rep = replicated_state(self.solvers[0]) if (self.scene.polygons or len(self.scene.circles_r)) else None
         self.solvers = []
-        self._build(replace(self.scene, particles=pos), prev)
+        self._build(replace(self.scene, particles=pos), prev, rep)

@@ -56,6 +56,9 @@ def _worker(rank, world, port, case, q):
         else:  # free particles pile up and spread sideways: ownership has to follow (rebalance over the group)
             sc = scenes.c2_free_particles(80, 30)
             sc.bounds = (0.0, 0.0, 48.0, 12.0)
+            if case == "free_circles":  # replicated Circles in the pile: their state must survive the re-partition
+                sc.circles_pos = np.array([[18.0, 10.5], [24.0, 10.8], [30.0, 10.2]], f32)
+                sc.circles_r = np.array([0.9, 0.6, 1.1], f32)
             sv = strips.StripSolver(sc, rank, world, 0, dist, band=4.0)
             n_updates, rebalanced, sent = 150, 0, (0, 0)
             for _ in range(n_updates):
@@ -66,13 +69,13 @@ def _worker(rank, world, port, case, q):
         pos, prev = sv.read_particles()
         gpos, gprev = strips.gather_global_state(dist, world, 0, sv.part.global_index, pos, prev, sc.n_particles)
         ok = True
-        if rank == 0 or case == "circles":
+        if rank == 0 or case in ("circles", "free_circles"):
             ref = Solver()
             sc.load_into(ref)
             ref.update(sc.dt, n=n_updates)
             rp, rq = ref.read_particles()
             ok = np.array_equal(gpos.view(np.uint32), rp.view(np.uint32)) and np.array_equal(gprev.view(np.uint32), rq.view(np.uint32))
-            if case == "circles":  # every rank's copy of the Circles equals the unsharded ones
+            if case in ("circles", "free_circles"):  # every rank's copy of the Circles equals the unsharded ones
                 a, b = sv.read_circles(), ref.read_circles()
                 ok = ok and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
                 moved = not np.array_equal(b[0][:, 0], sc.circles_pos[:, 0])  # the discs pushed them sideways
@@ -97,7 +100,7 @@ def _run(world, case, extra_env=None):
     try:
         ctx = mp.get_context("spawn")
         q = ctx.Queue()
-        port = 33500 + (os.getpid() % 2000) + 7 * world + {"bodies": 11, "polygons": 23, "circles": 37}.get(case, 0)
+        port = 33500 + (os.getpid() % 2000) + 7 * world + {"bodies": 11, "polygons": 23, "circles": 37, "free_circles": 51}.get(case, 0)
         procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
         for p in procs:
             p.start()
@@ -131,8 +134,9 @@ def test_nccl_strip_solvers_match_the_single_solver_bit_for_bit(world, extra):
     assert all(r[4] > 0 for r in res), "the substeps did not run as a captured graph"
 
 
-def test_nccl_strip_solvers_rebalance_over_the_process_group():
-    res = _run(3, "free")
+@pytest.mark.parametrize("case", ["free", "free_circles"])
+def test_nccl_strip_solvers_rebalance_over_the_process_group(case):
+    res = _run(3, case)
     assert all(ok is True for _, ok, *_ in res), res
     assert res[0][3] > 0, "the scene never needed rebalancing: nothing was tested"
 

@@ -481,8 +481,6 @@ def test_random_strip_field_is_bit_identical_to_single_solver(seed):
             pytest.skip(f"a disc moved {moved:.2f} between two polls: outside the rebalance contract (band {band:.2f})")
         before = after
         if grp.needs_rebalance():
-            if replicated:
-                pytest.skip("rebalance() does not carry circle / polygon state yet")
             try:
                 grp.rebalance()
             except ValueError as e:
