@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <sys/mman.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <map>
@@ -166,17 +167,30 @@ void run_batch(std::vector<Cta> &ctas, uint32_t threads, size_t smem) {
             remaining++;
         }
     }
+    // CUEMU_ORDER: the order in which runnable threads are resumed.  0 = thread 0 first (default), 1 = last thread
+    // first, 2 = a new pseudo-random order every sweep.  A device promises no order at all, so results must not
+    // depend on it: the test suite runs under all three.
+    static const int order_mode = getenv("CUEMU_ORDER") ? atoi(getenv("CUEMU_ORDER")) : 0;
+    static uint64_t rng = 0x9E3779B97F4A7C15ull;
+    std::vector<Fiber *> order;
+    for (Cta &c : ctas)
+        for (Fiber *f : c.fibers) order.push_back(f);
+    if (order_mode == 1) std::reverse(order.begin(), order.end());
     auto last_progress = std::chrono::steady_clock::now();
     while (true) {
         const uint64_t ev0 = g.events, spins0 = g_spins;
         uint32_t alive = 0;
-        for (Cta &c : ctas)
-            for (Fiber *f : c.fibers) {
-                if (f->done) continue;
-                alive++;
-                if (f->at_barrier) continue;
-                resume(f);
+        if (order_mode == 2)
+            for (size_t k = order.size(); k > 1; k--) {
+                rng ^= rng << 13, rng ^= rng >> 7, rng ^= rng << 17;
+                std::swap(order[k - 1], order[rng % k]);
             }
+        for (Fiber *f : order) {
+            if (f->done) continue;
+            alive++;
+            if (f->at_barrier) continue;
+            resume(f);
+        }
         if (!alive) break;
         if (g.events != ev0) {
             last_progress = std::chrono::steady_clock::now();

@@ -88,6 +88,16 @@ def test_parity_suite_on_emulator_plain_launches(emu_lib):
                               extra_env={"BENDY_SMALL_SCENE": "0", "BENDY_SCAN_FUSED": "0", "BENDY_PDL": "0"})
 
 
+@pytest.mark.parametrize("order", ["1", "2"])
+def test_results_do_not_depend_on_the_thread_schedule(emu_lib, order):
+    """A device promises no execution order.  The emulation resumes runnable threads last-first (1) or in a new
+    pseudo-random order every sweep (2): every bit-exact parity test must still pass, i.e. slot orders, atomic
+    arrival orders and near-list orders never leak into results."""
+    run_gpu_tests_on_emulator(emu_lib, ["tests/test_gpu_parity.py", "tests/test_z_gpu_variants.py", "tests/test_golden.py",
+                                        "tests/test_z_gpu_strips_replicated.py", "-k", "not full_size"],
+                              extra_env={"CUEMU_ORDER": order})
+
+
 def test_limits_strips_snapshot_golden_on_emulator(emu_lib):
     run_gpu_tests_on_emulator(emu_lib, ["tests/test_gpu_limits.py", "tests/test_gpu_strips.py", "tests/test_snapshot.py",
                                         "tests/test_golden.py", "tests/test_z_gpu_strips_replicated.py", "-k", "not 4200 and not nccl"])
