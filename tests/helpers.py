@@ -120,6 +120,7 @@ def rel_err(got, ref, scale):
     with np.errstate(invalid="ignore"):
         e = np.abs(got - ref) / den
     e[np.isnan(got) & np.isnan(ref)] = 0.0
+    e[got == ref] = 0.0  # equal infinities (inf - inf is NaN above)
     return float(np.nanmax(e)) if e.size else 0.0
 
 
