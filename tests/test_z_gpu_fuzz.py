@@ -498,3 +498,44 @@ def test_random_strip_field_is_bit_identical_to_single_solver(seed):
         for j in range(len(sc.polygons)):
             a, b = sv.read_polygon(j), ref.read_polygon(j)
             assert max_ulp(a[0], b[0]) == 0 and max_ulp(a[1], b[1]) == 0 and max_ulp(a[2], b[2]) == 0, (seed, "polygon", j)
+
+
+# ------------------------------------------------------------------------------------------------
+# what the reference never validates: the pub fields and dt may hold anything (solver.rs:21-23,106)
+ODD_BOUNDS = [(0, 0, -10, 20), (5, 5, 0, 0), (0, 0, np.inf, 50), (np.nan, 0, 50, 50), (0, 0, 1e-3, 1e-3), (-1e6, -1e6, 2e6, 2e6),
+              (0, 0, 3e38, 3e38)]
+ODD_GRAVITY = [(np.nan, 0), (np.inf, 1), (0, -1e30), (1e-40, 1e-40)]
+ODD_DT = [1e-9, 10.0, np.inf, 0.0, -0.01]
+
+
+@pytest.mark.parametrize("seed", range(max(6, N_SEEDS // 4)))
+def test_odd_bounds_gravity_and_dt_match_the_oracle(seed):
+    for variant in range(3):
+        g, o, info = build_world(seed * 5 + 2, disable=("inv_mass",))
+        rng = np.random.default_rng(seed * 7 + variant)
+        dt = float(f32(1 / 120))
+        if variant == 0:
+            b = ODD_BOUNDS[int(rng.integers(len(ODD_BOUNDS)))]
+            g.bounds.pos[:] = b[:2]
+            g.bounds.size[:] = b[2:]
+            o.set_bounds(*[float(f32(v)) for v in b])
+            if info["radius"] > 0 and info["nP"]:  # the broadphase grid follows the bounds
+                o.set_point_rank(g.point_rank())
+                o.set_grid(*g.grid())
+        elif variant == 1:
+            gv = ODD_GRAVITY[int(rng.integers(len(ODD_GRAVITY)))]
+            g.gravity = np.array(gv, f32)
+            o.set_gravity(float(f32(gv[0])), float(f32(gv[1])))
+        else:
+            dt = float(f32(ODD_DT[int(rng.integers(len(ODD_DT)))]))
+        for k in range(5):
+            g.update(dt)
+            o.update(dt)
+            try:
+                st = compare_state(g, o, max(info["scale"], 1.0), 1e-5, what=f"seed {seed} variant {variant} update {k + 1} {info}")
+            except BendyError as e:
+                if info["contact"] and "polygon broadphase overflow" in str(e):
+                    break
+                raise
+            if info["exact"]:
+                assert all(v == 0 for v in st.values()), (seed, variant, k, st)
