@@ -127,6 +127,12 @@ def lib() -> C.CDLL:
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(bendy2d_b200 has no CPU fallback)")
+    # tests/cuemu builds the same sources against a CPU emulation of CUDA to check kernel logic without a GPU.
+    # That library is test infrastructure: it is only accepted when the test harness says so explicitly, so
+    # that no configuration mistake can turn it into a CPU path of the product.
+    if os.path.basename(LIB_PATH).endswith("_emu.so") and os.environ.get("BENDY_CUDA_EMU") != "1":
+        raise ImportError(f"{LIB_PATH} is the CPU emulation build used by the tests, not a product library "
+                          "(bendy2d_b200 has no CPU fallback)")
     L = C.CDLL(LIB_PATH)
     for name, (res, args) in signatures().items():
         fn = getattr(L, name)  # AttributeError here = header and library out of sync

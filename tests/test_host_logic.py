@@ -169,3 +169,19 @@ def test_rust_sys_crate_declares_the_header_symbol_for_symbol():
     assert set(c_decl) == set(r_decl), (sorted(set(c_decl) - set(r_decl)), sorted(set(r_decl) - set(c_decl)))
     wrong = {k: (c_decl[k], r_decl[k]) for k in c_decl if c_decl[k] != r_decl[k]}
     assert not wrong, wrong
+
+
+def test_the_emulation_build_is_not_accepted_as_a_product_library(tmp_path):
+    """tests/cuemu's library only loads when the test harness opts in (BENDY_CUDA_EMU=1): a stray
+    BENDY2D_B200_LIB can never turn it into a CPU path of the product."""
+    import subprocess
+    import sys
+
+    fake = tmp_path / "libbendy2d_b200_emu.so"
+    fake.write_bytes(b"")
+    env = dict(os.environ, BENDY2D_B200_LIB=str(fake))
+    env.pop("BENDY_CUDA_EMU", None)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", "from bendy2d_b200 import _lib; _lib.lib()"], cwd=root, env=env,
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
