@@ -44,3 +44,11 @@ for tool in memcheck racecheck; do
       -k "pool_flushes or 768 or strip_variants" > gpurun_out/r2_sanitizer_$tool.log 2>&1
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" gpurun_out/r2_sanitizer_$tool.log | tee -a $OUT
 done
+# 5. refresh the launch list of the default path (profiles/r1_launches_* predate the fused polygon prepare kernel) and
+#    one full capture of the main-chain kernels; numbers printed under ncu are never bench values
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 208 --csv --log-file gpurun_out/r2_launches_bench_steps2.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-scaling-ref > gpurun_out/r2_ncu_bench.log 2>&1
+python profiles/summarize_launches.py gpurun_out/r2_launches_bench_steps2.csv > gpurun_out/r2_launches_summary.txt 2>&1
+tail -20 gpurun_out/r2_launches_summary.txt | tee -a $OUT
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k2_narrow|k3_links_local|k2_scan|k2_scatter" -s 40 -c 12 \
+    -o gpurun_out/r2_full python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-scaling-ref > gpurun_out/r2_ncu_full.log 2>&1
