@@ -463,7 +463,7 @@ static void ext_disc_contacts(bo_world &w, const std::vector<V2> &QC) {
 
 // ext — PARITY UNPINNED BY THE REFERENCE (a free particle never meets a polygon there).
 // Spec: static convex polygons are immovable obstacles for free particles.
-// For a particle q whose position lies in the polygon's AABB: per edge e=(a,b) build the inward
+// For a particle q whose position lies in the polygon's AABB (points and centre): per edge e=(a,b) build the inward
 // normal exactly as polygon.rs:175-181 does with the edge start as the on-line point; q is inside
 // iff every signed inward distance is > 0; the closest edge (smallest distance, lowest index on
 // ties) receives q via the reference's projection polygon.rs:206-209
@@ -489,6 +489,11 @@ static void ext_polygon_contacts(bo_world &w) {
             b.x1 = std::fmax(b.x1, pt.pos.x);
             b.y1 = std::fmax(b.y1, pt.pos.y);
         }
+        // the AABB covers the polygon's points AND its centre (the one solve_links computed, polygon.rs:219):
+        // the inward normals are built from that centre, and after a polygon-polygon contact has squashed a
+        // static polygon the centre can lie outside the hull of the points
+        b.x0 = std::fmin(b.x0, P.center.x), b.y0 = std::fmin(b.y0, P.center.y);
+        b.x1 = std::fmax(b.x1, P.center.x), b.y1 = std::fmax(b.y1, P.center.y);
         boxes[k] = b;
     }
     // coarse bins over the polygon boxes so the oracle stays O(n) at test sizes

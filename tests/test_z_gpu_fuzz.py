@@ -199,7 +199,9 @@ def build_world(seed, disable=()):
 
 # seeds that once failed stay in the default run: 278 = two overlapping static obstacles, a particle pushed out of
 # the first lands inside the AABB of the second (the entry-candidate rule of the contact extension)
-SEEDS = sorted(set(range(N_SEEDS)) | {278})
+# 5273 = a static obstacle squashed by a dynamic polygon until its centre lies outside its hull: the obstacle's AABB
+# is that of its points AND its centre (a particle above the sliver is "inside" by the centre-based normals)
+SEEDS = sorted(set(range(N_SEEDS)) | {278, 5273})
 
 
 @pytest.mark.parametrize("seed", SEEDS)
