@@ -122,6 +122,11 @@ def _run(world, case, extra_env=None):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+        import glob
+
+        for d in glob.glob("/tmp/cuemu_nccl_*"):  # the stub's FIFO directories (one per communicator)
+            if any(d.startswith(f"/tmp/cuemu_nccl_{p.pid}_") for p in procs):
+                shutil.rmtree(d, ignore_errors=True)
     return sorted(res)
 
 
