@@ -97,6 +97,7 @@ def _run(world, case, extra_env=None):
     env.update(extra_env or {})
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
+    procs = []
     try:
         ctx = mp.get_context("spawn")
         q = ctx.Queue()
