@@ -5,6 +5,10 @@ body count by centroid x.  Every substep each strip sends the owned discs that l
 neighbours' halo bands; they become read-only ghost discs of the neighbour's broadphase grid.
 The Jacobi contact rule only ever moves a disc on the rank that owns it, so no corrections travel
 back, and because all sums are order-free the sharded run is bit-identical to the 1-GPU run.
+Circles and polygons are replicated on every strip; the fixed-point corrections a strip's own discs
+collect for the Circles are summed over the strips by the library (ncclAllReduce / the group's sum)
+before they are applied, so every copy stays identical to the unsharded run.  Inverse masses are not
+supported in strips.
 
   StripSolver      one process per GPU, halo over NCCL (send/recv on the solver's stream, issued by
                    libbendy2d_b200.so inside the captured substep graph); torch.distributed only
