@@ -190,6 +190,8 @@ static inline float __uint_as_float(uint32_t a) { return cuemu::unpack<float>(cu
 static inline float __int_as_float(int a) { return cuemu::unpack<float>(cuemu::pack(a)); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 template <typename T>
 static inline T __ldcg(const T *p) {
     return *p;
@@ -205,6 +207,12 @@ template <typename T, typename U>
 static inline T atomicAdd(T *p, U v) {
     T old = *p;
     *p = (T)(old + (T)v);
+    return old;
+}
+template <typename T, typename U, typename V>
+static inline T atomicCAS(T *p, U expected, V desired) {
+    T old = *p;
+    if (old == (T)expected) *p = (T)desired;
     return old;
 }
 template <typename T, typename U>
@@ -278,6 +286,15 @@ static inline uint32_t __reduce_min_sync(uint32_t mask, uint32_t v) {
     uint32_t r = 0xFFFFFFFFu;
     for (uint32_t l = 0; l < 32; l++)
         if ((part >> l) & 1u) r = std::min(r, (uint32_t)s.vals[l]);
+    cuemu::warp_done(s, part);
+    return r;
+}
+static inline uint32_t __reduce_max_sync(uint32_t mask, uint32_t v) {
+    uint32_t part;
+    cuemu::WarpSlot &s = cuemu::warp_arrive(mask, v, &part);
+    uint32_t r = 0u;
+    for (uint32_t l = 0; l < 32; l++)
+        if ((part >> l) & 1u) r = std::max(r, (uint32_t)s.vals[l]);
     cuemu::warp_done(s, part);
     return r;
 }
