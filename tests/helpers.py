@@ -130,7 +130,7 @@ def compare_state(gpu, o, scale, tol=1e-5, what=""):
     op, oq = o.particles()
     stats = {"ulp_pos": max_ulp(gp, op), "ulp_prev": max_ulp(gq, oq)}
     assert rel_err(gp, op, scale) <= tol, f"{what} particle pos: {stats}"
-    assert rel_err(gp - gq, op - oq, scale) <= tol * 50, f"{what} particle velocity: {stats}"
+    assert rel_err(gp - gq, op - oq, scale) <= tol, f"{what} particle velocity: {stats}"
     if o.circle_len():
         cp, cq, _ = gpu.read_circles()
         ocp, ocq, _ = o.circles()
