@@ -91,6 +91,7 @@ def signatures():
         "bendy_set_particle_inv_mass": (i, [vp, sz, sz, f32p]),
         "bendy_set_circle_inv_mass": (i, [vp, sz, sz, f32p]),
         "bendy_set_plan_params": (i, [vp, u32, u32]),
+        "bendy_set_link_schedule": (i, [vp, i]),
         "bendy_get_schedule_info": (i, [vp, C.POINTER(ScheduleInfo)]),
         "bendy_get_link_order": (i, [vp, u32p, sz]),
         "bendy_get_point_rank": (i, [vp, u32p, sz]),
@@ -112,6 +113,7 @@ def signatures():
         "bendy_update_group": (i, [C.POINTER(vp), i, u32, fl, fl, fl, fl, fl, fl, fl]),
         "bendy_halo_stats": (i, [vp, u32p, u32p, u32p, u32p]),
         "bendy_plan_links": (i, [sz, u32p, sz, u32, u32, u32p, u32p, u32p, u32p, C.POINTER(ScheduleInfo)]),
+        "bendy_plan_links_scheduled": (i, [sz, u32p, sz, u32, u32, i, u32p, u32p, u32p, u32p, C.POINTER(ScheduleInfo)]),
     }
     return _SIGS
 

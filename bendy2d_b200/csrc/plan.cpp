@@ -151,14 +151,44 @@ bool plan_links(size_t n_points, const uint32_t *ab, const float *len, size_t n_
     // extra colour it has not used yet, and the link takes the larger of its two ends' (so the links at a
     // vertex get strictly increasing colours, which is all a colouring needs).  The reference relaxes any
     // graph (solver.rs:144-146); so does this schedule - a hub of degree d costs about d launches.
-    std::vector<ColourMask> lmask(n_linked), gmask;
+    std::vector<ColourMask> lmask(pp.reference_order ? 0 : n_linked), gmask;
     std::vector<uint32_t> gnext;  // per vertex: first extra global colour (>= 256) not used at it yet
     std::vector<uint32_t> colour(n_links);
     std::vector<uint8_t> is_global(n_links, 0);
     uint32_t C = 0, G = 0;
     size_t n_global = 0;
     (void)err;
-    for (size_t k = 0; k < n_links; k++) {
+    if (pp.reference_order) {
+        // Dependency levels in insertion order (see PlanParams::reference_order).  Partitions are independent
+        // of each other only while no link crosses them: then the levels are taken per partition and run as the
+        // partition kernel's colours.  A crossing link, or a partition that needs more levels than the kernel's
+        // colour table holds, makes every link a "global" one: one launch per level over the whole graph.
+        std::vector<uint32_t> next(n_linked, 0u);
+        bool local_ok = true;
+        for (size_t k = 0; k < n_links && local_ok; k++) {
+            const uint32_t a = P.rank[ab[2 * k]], b = P.rank[ab[2 * k + 1]];
+            if (part_of[a] != part_of[b]) local_ok = false;
+            const uint32_t lv = std::max(next[a], next[b]);
+            if (lv >= kMaxLocalColours) local_ok = false;
+            colour[k] = lv;
+            next[a] = next[b] = lv + 1;
+            C = std::max(C, lv + 1);
+        }
+        if (!local_ok) {
+            std::fill(next.begin(), next.end(), 0u);
+            C = 0;
+            for (size_t k = 0; k < n_links; k++) {
+                const uint32_t a = P.rank[ab[2 * k]], b = P.rank[ab[2 * k + 1]];
+                const uint32_t lv = std::max(next[a], next[b]);
+                colour[k] = lv;
+                next[a] = next[b] = lv + 1;
+                is_global[k] = 1;
+                G = std::max(G, lv + 1);
+            }
+            n_global = n_links;
+        }
+    }
+    for (size_t k = 0; k < n_links && !pp.reference_order; k++) {
         uint32_t a = P.rank[ab[2 * k]], b = P.rank[ab[2 * k + 1]];
         int c = -1;
         if (part_of[a] == part_of[b]) {

@@ -33,6 +33,14 @@ constexpr uint32_t kMaxLocalColours = 255;
 struct PlanParams {
     uint32_t pack_points = 512;  // keep adding whole components to a partition up to this many points
     uint32_t max_points = 4096;  // hard cap (shared memory: 8 B per point)
+    // false: greedy edge colouring (few colours; results equal the reference fed the links in the exported
+    //        colour order, the contract of north_star);
+    // true:  REFERENCE ORDER - colours are dependency levels in insertion order: level = max(next[a], next[b]),
+    //        next[a] = next[b] = level + 1.  Every link then runs after all EARLIER links that share a vertex
+    //        with it and links of one level are vertex-disjoint, so the level-parallel schedule is arithmetically
+    //        identical to the reference's sequential walk in insertion order (solver.rs:144-146) - at the price
+    //        of more colours (a 20x20 lattice: ~60 levels instead of 8 colours).
+    bool reference_order = false;
 };
 
 struct LinkPlan {

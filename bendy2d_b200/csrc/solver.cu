@@ -1507,7 +1507,8 @@ int bendy_save_snapshot(bendy_solver *s, const char *path) {
     memcpy(h.magic, kSnapMagic, 8);
     h.version = 1, h.sub_steps = s->sub_steps;
     h.particle_radius = s->particle_radius, h.grid_cell = s->grid_cell;
-    h.polygon_contact = s->polygon_contact, h.pack_points = s->plan_params.pack_points;
+    h.polygon_contact = (s->polygon_contact ? 1u : 0u) | (s->plan_params.reference_order ? 2u : 0u);  // bit 1: link schedule
+    h.pack_points = s->plan_params.pack_points;
     h.max_points = s->plan_params.max_points, h.has_last = s->have_last_args;
     for (int i = 0; i < 7; i++) h.last[i] = s->last_args[i];
     const uint64_t n[9] = {s->p_pos.size(), s->c_pos.size(), s->polys.size(), s->g_pos.size(), s->pl_len.size(),
@@ -1612,7 +1613,8 @@ bendy_solver *bendy_load_snapshot(const char *path, int device) {
             if (s->g_acc[P.start + v].x != 0.f || s->g_acc[P.start + v].y != 0.f) s->any_acc = true;
     s->sub_steps = (uint16_t)h.sub_steps;
     s->particle_radius = h.particle_radius, s->grid_cell = h.grid_cell;
-    s->polygon_contact = h.polygon_contact != 0;
+    s->polygon_contact = (h.polygon_contact & 1u) != 0;
+    s->plan_params.reference_order = (h.polygon_contact & 2u) != 0;
     s->plan_params.pack_points = h.pack_points, s->plan_params.max_points = h.max_points;
     s->have_last_args = h.has_last != 0;
     for (int i = 0; i < 7; i++) s->last_args[i] = h.last[i];
@@ -1984,6 +1986,19 @@ int bendy_set_plan_params(bendy_solver *s, uint32_t pack_points, uint32_t max_po
     return BENDY_OK;
 }
 
+int bendy_set_link_schedule(bendy_solver *s, int mode) {
+    NEED(s);
+    OPS;
+    if (mode != BENDY_LINKS_COLOURED && mode != BENDY_LINKS_REFERENCE_ORDER)
+        return ops.fail(BENDY_ERR_ARG, "bendy_set_link_schedule: mode is BENDY_LINKS_COLOURED or BENDY_LINKS_REFERENCE_ORDER");
+    const bool ref = mode == BENDY_LINKS_REFERENCE_ORDER;
+    if (ref != s->plan_params.reference_order) {
+        s->plan_params.reference_order = ref;
+        s->topo_dirty = true;
+    }
+    return BENDY_OK;
+}
+
 // ---- schedule export ----------------------------------------------------------------------------
 static void fill_info(const LinkPlan &P, const LinkPlan *G, bendy_schedule_info *out) {
     std::memset(out, 0, sizeof *out);
@@ -2297,7 +2312,15 @@ int bendy_update_group(bendy_solver **group, int n, uint32_t n_updates, float dt
 int bendy_plan_links(size_t n_points, const uint32_t *ab, size_t n_links, uint32_t pack_points, uint32_t max_points,
                      uint32_t *rank, uint32_t *perm, uint32_t *link_colour, uint32_t *link_partition,
                      bendy_schedule_info *info) {
+    return bendy_plan_links_scheduled(n_points, ab, n_links, pack_points, max_points, BENDY_LINKS_COLOURED, rank, perm,
+                                      link_colour, link_partition, info);
+}
+
+int bendy_plan_links_scheduled(size_t n_points, const uint32_t *ab, size_t n_links, uint32_t pack_points,
+                               uint32_t max_points, int link_schedule, uint32_t *rank, uint32_t *perm,
+                               uint32_t *link_colour, uint32_t *link_partition, bendy_schedule_info *info) {
     if (n_links && !ab) return BENDY_ERR_ARG;
+    if (link_schedule != BENDY_LINKS_COLOURED && link_schedule != BENDY_LINKS_REFERENCE_ORDER) return BENDY_ERR_ARG;
     for (size_t k = 0; k < n_links; k++)
         if (!(ab[2 * k] < ab[2 * k + 1]) || !(ab[2 * k + 1] < n_points)) {
             g_last_error = "bendy_plan_links: link needs a < b < n_points";
@@ -2310,6 +2333,7 @@ int bendy_plan_links(size_t n_points, const uint32_t *ab, size_t n_links, uint32
     PlanParams pp;
     if (pack_points) pp.pack_points = pack_points;
     if (max_points) pp.max_points = max_points;
+    pp.reference_order = link_schedule == BENDY_LINKS_REFERENCE_ORDER;
     std::vector<float> len(n_links, 1.0f);
     LinkPlan P;
     std::string err;

@@ -11,7 +11,7 @@ Layout (writer: bendy2d_b200/csrc/solver.cu):
 
     magic "B2DSNAP1"
     u32 version (=1), sub_steps | f32 particle_radius, grid_cell
-    u32 polygon_contact, pack_points, max_points, has_last_update
+    u32 flags (bit 0 polygon_contact, bit 1 reference-order link schedule), pack_points, max_points, has_last_update
     f32 last update: dt, gravity x, y, bounds x, y, w, h, 0
     u64 n_particles, n_circles, n_polygons, n_polygon_points, n_particle_links, n_circle_links,
         n_polygon_links, has_particle_inv_mass, has_circle_inv_mass
@@ -53,6 +53,7 @@ class Snapshot:
     particle_radius: float = 0.0
     grid_cell: float = 0.0
     polygon_contact: bool = False
+    reference_link_order: bool = False
     pack_points: int = 512
     max_points: int = 4096
     last_update: Optional[np.ndarray] = None  # dt, gx, gy, bx, by, bw, bh of the last update(), or None
@@ -140,7 +141,7 @@ class Snapshot:
                   len(self.particle_links_len), len(self.circle_links_len), len(self.poly_links_len),
                   int(self.particles_inv_mass is not None), int(self.circles_inv_mass is not None))
         head = _HEADER.pack(MAGIC, VERSION, self.sub_steps, self.particle_radius, self.grid_cell,
-                            int(self.polygon_contact), self.pack_points, self.max_points,
+                            int(self.polygon_contact) | (2 if self.reference_link_order else 0), self.pack_points, self.max_points,
                             int(self.last_update is not None), *[float(x) for x in last], *counts)
         table = np.zeros((self.n_polygons, 7), u32)
         if self.n_polygons:
@@ -191,7 +192,8 @@ class Snapshot:
             off += nbytes
             return a if shape is None else a.reshape(shape)
 
-        s = Snapshot(sub_steps=sub_steps, particle_radius=rp, grid_cell=cell, polygon_contact=bool(contact),
+        s = Snapshot(sub_steps=sub_steps, particle_radius=rp, grid_cell=cell, polygon_contact=bool(contact & 1),
+                     reference_link_order=bool(contact & 2),
                      pack_points=pack, max_points=maxp, last_update=last[:7].copy() if has_last else None)
         s.particles_pos, s.particles_prev = take(2 * nP, f32, (-1, 2)), take(2 * nP, f32, (-1, 2))
         s.particles_inv_mass = take(nP, f32) if has_pk else None
@@ -241,6 +243,8 @@ class Snapshot:
         if self.grid_cell:
             solver.set_grid_cell(self.grid_cell)
         solver.set_polygon_contact(self.polygon_contact)
+        if self.reference_link_order:
+            solver.set_link_schedule("reference")
         if self.particles_inv_mass is not None:
             solver.set_particle_inv_mass(self.particles_inv_mass)
         if self.circles_inv_mass is not None:

@@ -398,6 +398,15 @@ class Solver:
     def set_plan_params(self, pack_points: int = 0, max_points: int = 0):
         self._ck(self._L.bendy_set_plan_params(self._h, pack_points, max_points))
 
+    def set_link_schedule(self, mode: str = "coloured"):
+        """"coloured" (default: greedy colouring, results = the reference fed the links in `link_order()`),
+        or "reference": dependency-level colours, results = the reference's own insertion-order walk
+        (solver.rs:143-146) bit for bit, at the price of more colours."""
+        modes = {"coloured": 0, "reference": 1}
+        if mode not in modes:
+            raise ValueError(f"link schedule {mode!r}: one of {sorted(modes)}")
+        self._ck(self._L.bendy_set_link_schedule(self._h, modes[mode]))
+
     # ---- schedule export (for the oracle replay) -------------------------------------------------
     def schedule_info(self) -> dict:
         info = _lib.ScheduleInfo()
@@ -462,7 +471,7 @@ class Solver:
         return pos.value, prev.value, n.value
 
 
-def plan_links(n_points: int, ab, pack_points: int = 0, max_points: int = 0):
+def plan_links(n_points: int, ab, pack_points: int = 0, max_points: int = 0, reference_order: bool = False):
     """Host-only link planner (no GPU needed): returns rank, perm, colour, partition, info."""
     L = _lib.lib()
     ab = _u(np.asarray(ab).reshape(-1, 2))
@@ -470,8 +479,8 @@ def plan_links(n_points: int, ab, pack_points: int = 0, max_points: int = 0):
     rank, perm = np.empty(n_points, np.uint32), np.empty(n, np.uint32)
     colour, part = np.empty(n, np.uint32), np.empty(n, np.uint32)
     info = _lib.ScheduleInfo()
-    rc = L.bendy_plan_links(n_points, _up(ab), n, pack_points, max_points, _up(rank), _up(perm), _up(colour),
-                            _up(part), C.byref(info))
+    rc = L.bendy_plan_links_scheduled(n_points, _up(ab), n, pack_points, max_points, 1 if reference_order else 0,
+                                      _up(rank), _up(perm), _up(colour), _up(part), C.byref(info))
     if rc != 0:
         msg = (L.bendy_last_error(None) or b"").decode()
         raise (LinkPanic if rc == -2 else BendyError)(rc, msg)

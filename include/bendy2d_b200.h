@@ -125,6 +125,15 @@ int bendy_set_circle_inv_mass(bendy_solver *s, size_t first, size_t n, const flo
 /* planner knobs: points per shared-memory partition (pack target, hard cap); 0 keeps the default (512, 4096).
  * Limits: pack_points <= 16384, 2 <= max_points <= 16384 (one partition = one CTA's shared memory). */
 int bendy_set_plan_params(bendy_solver *s, uint32_t pack_points, uint32_t max_points);
+/* Order in which the particle links are relaxed (solver.rs:143-146 walks them sequentially in insertion order).
+ * BENDY_LINKS_COLOURED (default): greedy graph colouring, few colours; the results equal the reference fed the
+ *   links in the order bendy_get_link_order exports (the contract: "fed links in the same colour order").
+ * BENDY_LINKS_REFERENCE_ORDER: dependency-level colours - every link runs after all EARLIER links that share a
+ *   point with it, so the results equal the reference's own insertion-order walk bit for bit, whatever order
+ *   the user added the links in; costs more colours (one CTA barrier or one launch each). */
+#define BENDY_LINKS_COLOURED 0
+#define BENDY_LINKS_REFERENCE_ORDER 1
+int bendy_set_link_schedule(bendy_solver *s, int mode);
 
 /* ---------------------------------------------------------------- schedule export (parity replay) */
 typedef struct bendy_schedule_info {
@@ -226,6 +235,10 @@ int bendy_get_device_buffers(bendy_solver *s, void **pos, void **prev, size_t *n
 int bendy_plan_links(size_t n_points, const uint32_t *ab, size_t n_links, uint32_t pack_points,
                      uint32_t max_points, uint32_t *rank, uint32_t *perm, uint32_t *link_colour,
                      uint32_t *link_partition, bendy_schedule_info *info);
+/* the same with the link schedule of bendy_set_link_schedule (BENDY_LINKS_COLOURED / BENDY_LINKS_REFERENCE_ORDER) */
+int bendy_plan_links_scheduled(size_t n_points, const uint32_t *ab, size_t n_links, uint32_t pack_points,
+                               uint32_t max_points, int link_schedule, uint32_t *rank, uint32_t *perm,
+                               uint32_t *link_colour, uint32_t *link_partition, bendy_schedule_info *info);
 
 #ifdef __cplusplus
 }

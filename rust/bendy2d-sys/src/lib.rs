@@ -13,6 +13,8 @@ pub const BENDY_ERR_LINK: c_int = -2;
 pub const BENDY_ERR_CUDA: c_int = -3;
 pub const BENDY_ERR_UNSUPPORTED: c_int = -4;
 pub const BENDY_ERR_NO_DEVICE: c_int = -5;
+pub const BENDY_LINKS_COLOURED: c_int = 0;
+pub const BENDY_LINKS_REFERENCE_ORDER: c_int = 1;
 
 #[repr(C)]
 #[derive(Debug, Default, Clone, Copy)]
@@ -80,6 +82,7 @@ extern "C" {
     pub fn bendy_set_particle_inv_mass(s: *mut bendy_solver, first: usize, n: usize, k: *const c_float) -> c_int;
     pub fn bendy_set_circle_inv_mass(s: *mut bendy_solver, first: usize, n: usize, k: *const c_float) -> c_int;
     pub fn bendy_set_plan_params(s: *mut bendy_solver, pack_points: u32, max_points: u32) -> c_int;
+    pub fn bendy_set_link_schedule(s: *mut bendy_solver, mode: c_int) -> c_int;
 
     pub fn bendy_get_schedule_info(s: *mut bendy_solver, out: *mut bendy_schedule_info) -> c_int;
     pub fn bendy_get_link_order(s: *mut bendy_solver, perm: *mut u32, n: usize) -> c_int;
@@ -114,4 +117,7 @@ extern "C" {
     pub fn bendy_plan_links(n_points: usize, ab: *const u32, n_links: usize, pack_points: u32, max_points: u32,
                             rank: *mut u32, perm: *mut u32, link_colour: *mut u32, link_partition: *mut u32,
                             info: *mut bendy_schedule_info) -> c_int;
+    pub fn bendy_plan_links_scheduled(n_points: usize, ab: *const u32, n_links: usize, pack_points: u32, max_points: u32,
+                                      link_schedule: c_int, rank: *mut u32, perm: *mut u32, link_colour: *mut u32,
+                                      link_partition: *mut u32, info: *mut bendy_schedule_info) -> c_int;
 }

@@ -36,6 +36,7 @@ int main(void) {
     rc |= bendy_set_particle_inv_mass(s, 0, 2, k);
     rc |= bendy_set_circle_inv_mass(s, 0, 1, k);
     rc |= bendy_set_plan_params(s, 0, 0);
+    rc |= bendy_set_link_schedule(s, BENDY_LINKS_COLOURED);
     rc |= bendy_update(s, 0.01f, 0.f, 98.2f, 0.f, 0.f, 100.f, 100.f);
     rc |= bendy_update_n(s, 2, 0.01f, 0.f, 98.2f, 0.f, 0.f, 100.f, 100.f);
     rc |= bendy_synchronize(s);
@@ -65,6 +66,7 @@ int main(void) {
     grp[0] = s;
     rc |= bendy_update_group(grp, 1, 1, 0.01f, 0.f, 98.2f, 0.f, 0.f, 100.f, 100.f);
     rc |= bendy_plan_links(2, ab, 1, 0, 0, rank, perm, NULL, NULL, &info);
+    rc |= bendy_plan_links_scheduled(2, ab, 1, 0, 0, BENDY_LINKS_REFERENCE_ORDER, rank, perm, NULL, NULL, &info);
     {
         float last[7];
         int valid = 0;

@@ -129,6 +129,32 @@ def test_bucket_parallel_relaxation_equals_the_sequential_walk(g):
     assert np.array_equal(seq.view(np.uint32), par.view(np.uint32))
 
 
+@given(graphs())
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+def test_reference_order_levels_respect_insertion_order(g):
+    """BENDY_LINKS_REFERENCE_ORDER: buckets are vertex-disjoint AND two links that share a point keep their
+    insertion order in the exported sequence - so the schedule equals the reference's walk (solver.rs:144-146)."""
+    n, ab, pack, maxp = g
+    ab = np.asarray(ab, np.int64).reshape(-1, 2)
+    rank, perm, colour, part, info = plan_links(n, ab, pack, maxp, reference_order=True)
+    m = len(ab)
+    assert sorted(perm.tolist()) == list(range(m))
+    local = part != GLOBAL
+    assert local.all() or (~local).all()  # levels per partition, or over the whole graph
+    key = np.where(local, part.astype(np.int64), -1) * (1 << 32) + colour
+    for k in np.unique(key):
+        ends = ab[key == k].ravel()
+        assert len(np.unique(ends)) == len(ends)
+    where = np.empty(m, np.int64)
+    where[perm] = np.arange(m)
+    last = {}
+    for k, (a, b) in enumerate(ab.tolist()):
+        for v in (a, b):
+            if v in last:
+                assert where[last[v]] < where[k], "a later link that shares a point ran first"
+            last[v] = k
+
+
 def test_hubs_beyond_the_colour_tables_spill_into_extra_global_colours():
     # a star of degree d needs exactly d colours; the partition kernel's table holds 255 (kernels.cuh
     # K3_MAX_COLOURS), the cross-partition masks another 256; whatever is left gets one extra colour each.
