@@ -169,19 +169,7 @@ struct bendy_solver {
     bool has_k = false;
     // grid
     DevBuf<uint32_t> d_cell_count, d_cell_start, d_tile_sum, d_sorted_id, d_slot_of;
-    DevBuf<uint32_t> d_scan_barrier;
-    uint32_t scan_fused_capacity = 0;  // CTAs of k2_scan_fused that can be resident at once
-    bool sort_fused = false;           // BENDY_SORT_FUSED=1: k2_scan_scatter_fused (scan + scatter in one launch)
-    bool sort_fused_force = false;     // BENDY_SORT_FUSED=2: skip the residency check (experiments; the barrier times out)
-    uint32_t sort_fused_capacity = 0;
-    bool scatter_ilp = false;          // BENDY_SCATTER_ILP=1: k2_scatter_ilp (4 discs per thread)
-    bool halo_fused = false;           // BENDY_HALO_FUSED=1: send-buffer reset + ghost histogram in one launch
-    bool narrow_dense = false;         // BENDY_NARROW_DENSE=1: k2_narrow_dense (lane-dense contact resolution)
-    bool scan_mt = false;              // BENDY_SCAN_MT=1: k2_scan_fused_mt<2|4> when one tile per CTA does not fit
-    uint32_t scan_mt_capacity[2] = {0, 0};  // resident CTAs of k2_scan_fused_mt<2>, <4>
-    uint32_t scan_tiles_per_cta = 1;
     uint32_t k3_threads = 128;  // BENDY_K3_THREADS
-    bool scatter_agg = false;   // BENDY_SCATTER_AGG
     bool halo_overlap = false;  // BENDY_HALO_OVERLAP
     bool small_scene = true;    // BENDY_SMALL_SCENE=0 forces the multi-kernel path for tiny scenes
     int pdl = 3;                // BENDY_PDL: 0 = off, 1 = programmatic dependent launch for links/scan/scatter,
@@ -381,12 +369,6 @@ int Ops::check_flags() {
     CK(cudaStreamSynchronize(s->stream));
     if (f) {
         CK(cudaMemsetAsync(s->d_flags.p, 0, sizeof(int), s->stream));
-        if (f & FLAG_GRID_BARRIER_TIMEOUT) {
-            s->sticky = BENDY_ERR_CUDA;
-            return fail(BENDY_ERR_CUDA,
-                        "a software grid barrier (BENDY_SCAN_MT / BENDY_SORT_FUSED kernels) timed out: not every CTA of "
-                        "the grid was resident; the state of the solver is invalid");
-        }
         // Only the particle-polygon contact (ext) takes its candidates from the tile lists.  The reference's
         // polygon<->polygon pass is exact whatever the bins hold: the pair pre-scan answers an overflowing
         // tile or an unbinned polygon with "start at row 0" and the pass itself compares all boxes.
@@ -721,43 +703,10 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
             s->n_cells = ncells;
             // n_cells + 1 counters (the extra cell collects non-finite points), padded to whole scan tiles
             s->n_scan_tiles = cdiv(ncells + 1, SCAN_TILE);
-            size_t padded = (size_t)s->n_scan_tiles * SCAN_TILE;
+            const size_t padded = (size_t)s->n_scan_tiles * SCAN_TILE;
             CK(s->d_cell_count.ensure(padded));
             CK(cudaMemsetAsync(s->d_cell_count.p, 0, padded * sizeof(uint32_t), s->stream));
             CK(s->d_cell_start.ensure(padded));
-            CK(s->d_scan_barrier.ensure(4));  // [0] k2_scan_fused*; [1..3] k2_scan_scatter_fused (scan, scatter, generation)
-            CK(cudaMemsetAsync(s->d_scan_barrier.p, 0, 4 * sizeof(uint32_t), s->stream));
-            if (!s->scan_fused_capacity) {
-                int per_sm = 0, sms = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_fused, SCAN_THREADS, 0));
-                CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-                s->scan_fused_capacity = (uint32_t)std::max(per_sm * sms, 1);
-                if (const char *v = getenv("BENDY_SCAN_FUSED"))
-                    if (atoi(v) == 0) s->scan_fused_capacity = 1;
-            }
-            // opt-in: several tiles per CTA so that a larger histogram still scans in one resident wave
-            s->scan_tiles_per_cta = 1;
-            if (s->scan_mt && (uint64_t)s->n_scan_tiles * 100 > (uint64_t)s->scan_fused_capacity * 85) {
-                if (!s->scan_mt_capacity[0]) {
-                    int per_sm = 0, sms = 0;
-                    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_fused_mt<2>, SCAN_THREADS, 0));
-                    s->scan_mt_capacity[0] = (uint32_t)std::max(per_sm * sms, 1);
-                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_fused_mt<4>, SCAN_THREADS, 0));
-                    s->scan_mt_capacity[1] = (uint32_t)std::max(per_sm * sms, 1);
-                }
-                for (uint32_t k = 0; k < 2 && s->scan_tiles_per_cta == 1; k++) {
-                    const uint32_t T = 2u << k;
-                    if ((uint64_t)cdiv(s->n_scan_tiles, T) * 100 <= (uint64_t)s->scan_mt_capacity[k] * 85) s->scan_tiles_per_cta = T;
-                }
-                if (s->scan_tiles_per_cta > 1) {  // whole CTAs: the extra tiles are empty cells behind the grid
-                    s->n_scan_tiles = cdiv(s->n_scan_tiles, s->scan_tiles_per_cta) * s->scan_tiles_per_cta;
-                    padded = (size_t)s->n_scan_tiles * SCAN_TILE;
-                    CK(s->d_cell_count.ensure(padded));
-                    CK(cudaMemsetAsync(s->d_cell_count.p, 0, padded * sizeof(uint32_t), s->stream));
-                    CK(s->d_cell_start.ensure(padded));
-                }
-            }
             CK(s->d_tile_sum.ensure(s->n_scan_tiles));
             CK(cudaMemsetAsync(s->d_tile_sum.p, 0, (size_t)s->n_scan_tiles * sizeof(uint32_t), s->stream));
             if (s->nC) {
@@ -868,6 +817,7 @@ SubstepCtx Ops::make_ctx() {
     c.ca = K3CountArgs{c.prm,
                        s->n_cells,
                        s->d_cell_count.p,
+                       s->d_tile_sum.p,
                        c.halo ? s->d_send[0].p : nullptr,
                        c.halo ? s->d_send[1].p : nullptr,
                        c.halo ? s->d_send_cnt.p : nullptr,
@@ -988,12 +938,6 @@ int Ops::launch_count_unlinked(const SubstepCtx &c) {
 
 // strips: my send buffers were consumed -> reset them; the received ghosts join the histogram
 int Ops::launch_halo_receive(const SubstepCtx &c, cudaStream_t q_clear) {
-    if (s->halo_fused && q_clear == c.st) {
-        const uint32_t n = std::max(s->ghost_cap, s->nP - s->nOwned);
-        LAUNCH(BENDY_K_HALO, launch_k(c.pdl > 0, k_halo_receive, cdiv(n, 256), 256, 0, c.st, s->d_send[0].p, s->d_send[1].p,
-                                      s->d_send_cnt.p, s->ghost_cap, c.pos, s->nOwned, s->nP, c.ca));
-        return BENDY_OK;
-    }
     LAUNCH(BENDY_K_HALO, k_halo_clear<<<cdiv(s->ghost_cap, 256), 256, 0, q_clear>>>(s->d_send[0].p, s->d_send[1].p,
                                                                                     s->d_send_cnt.p, s->ghost_cap));
     if (q_clear != c.st) {
@@ -1034,73 +978,22 @@ int Ops::launch_particle_links(const SubstepCtx &c, int phase, bool *ghosts_done
     return launch_count_unlinked(c);
 }
 
-// K2 grid build: exclusive scan of the cell histogram, then the counting-sort scatter
+// K2 grid build: exclusive scan of the cell histogram (one pass: the scan-tile totals came with the histogram),
+// then the counting-sort scatter
 int Ops::launch_grid_build(const SubstepCtx &c) {
     if (!c.discs) return BENDY_OK;
     cudaStream_t st = c.st;
-    if (s->sort_fused && s->scan_tiles_per_cta == 1) {
-        if (!s->sort_fused_capacity) {
-            int per_sm = 0, sms = 0;
-            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-            if (c.K)
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_scatter_fused<true>, SCAN_THREADS, 0));
-            else
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_scan_scatter_fused<false>, SCAN_THREADS, 0));
-            s->sort_fused_capacity = (uint32_t)std::max(per_sm * sms, 1);
-        }
-        if (s->sort_fused_force || (uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->sort_fused_capacity * 85) {
-            if (c.K)
-                LAUNCH(BENDY_K_GRID_BUILD,
-                       launch_k(c.pdl > 0, k2_scan_scatter_fused<true>, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
-                                s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p + 1, s->d_flags.p, c.pos, s->nP, c.prm, s->n_cells,
-                                s->d_sorted_pos.p, s->d_slot_of.p, s->d_sorted_id.p));
-            else
-                LAUNCH(BENDY_K_GRID_BUILD,
-                       launch_k(c.pdl > 0, k2_scan_scatter_fused<false>, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
-                                s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p + 1, s->d_flags.p, c.pos, s->nP, c.prm, s->n_cells,
-                                s->d_sorted_pos.p, s->d_slot_of.p, s->d_sorted_id.p));
-            return BENDY_OK;
-        }
-    }
-    if (s->scan_tiles_per_cta == 2) {
-        LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan_fused_mt<2>, s->n_scan_tiles / 2, SCAN_THREADS, 0, st,
-                                            s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p, s->d_flags.p));
-    } else if (s->scan_tiles_per_cta == 4) {
-        LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan_fused_mt<4>, s->n_scan_tiles / 4, SCAN_THREADS, 0, st,
-                                            s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p, s->d_flags.p));
-    } else if ((uint64_t)s->n_scan_tiles * 100 <= (uint64_t)s->scan_fused_capacity * 85) {
-        // every scan CTA fits on the device at once (15% spare; side-branch kernels finish on their own)
-        LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan_fused, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
-                                            s->d_tile_sum.p, s->d_cell_start.p, s->d_scan_barrier.p));
-    } else {
-        LAUNCH(BENDY_K_GRID_BUILD,
-               k2_tile_reduce<<<cdiv(s->n_scan_tiles, 8), 256, 0, st>>>(s->d_cell_count.p, s->n_scan_tiles, s->d_tile_sum.p));
-        LAUNCH(BENDY_K_GRID_BUILD,
-               k2_scan<<<s->n_scan_tiles, SCAN_THREADS, 0, st>>>(s->d_cell_count.p, s->d_tile_sum.p, s->d_cell_start.p));
-    }
-#define SCATTER(ID, AG)                                                                                              \
-    LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scatter<ID, AG>, cdiv(s->nP, 256), 256, 0, st, c.pos, s->nP, c.prm, \
-                                        s->n_cells, s->d_cell_start.p, s->d_scan_barrier.p, s->d_sorted_pos.p,          \
-                                        s->d_slot_of.p, s->d_sorted_id.p))
-    if (s->scatter_ilp) {
-        const uint32_t g4 = cdiv(s->nP, 256 * 4);
-        if (c.K)
-            LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scatter_ilp<true, 4>, g4, 256, 0, st, c.pos, s->nP, c.prm, s->n_cells,
-                                                s->d_cell_start.p, s->d_scan_barrier.p, s->d_sorted_pos.p, s->d_slot_of.p,
-                                                s->d_sorted_id.p));
-        else
-            LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scatter_ilp<false, 4>, g4, 256, 0, st, c.pos, s->nP, c.prm, s->n_cells,
-                                                s->d_cell_start.p, s->d_scan_barrier.p, s->d_sorted_pos.p, s->d_slot_of.p,
-                                                s->d_sorted_id.p));
-    } else if (c.K && s->scatter_agg)
-        SCATTER(true, true);
-    else if (c.K)
-        SCATTER(true, false);
-    else if (s->scatter_agg)
-        SCATTER(false, true);
+    LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scan, s->n_scan_tiles, SCAN_THREADS, 0, st, s->d_cell_count.p,
+                                        s->d_tile_sum.p, s->d_cell_start.p));
+    const uint32_t blocks = cdiv(std::max(s->nP, s->n_scan_tiles), 256);
+    if (c.K)
+        LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scatter<true>, blocks, 256, 0, st, c.pos, s->nP, c.prm, s->n_cells,
+                                            s->d_cell_start.p, s->d_tile_sum.p, s->n_scan_tiles, s->d_sorted_pos.p,
+                                            s->d_slot_of.p, s->d_sorted_id.p));
     else
-        SCATTER(false, false);
-#undef SCATTER
+        LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_scatter<false>, blocks, 256, 0, st, c.pos, s->nP, c.prm, s->n_cells,
+                                            s->d_cell_start.p, s->d_tile_sum.p, s->n_scan_tiles, s->d_sorted_pos.p,
+                                            s->d_slot_of.p, s->d_sorted_id.p));
     return BENDY_OK;
 }
 
@@ -1116,12 +1009,7 @@ int Ops::launch_collide_integrate_discs(const SubstepCtx &c, int phase) {
     const uint32_t blocks = cdiv(s->nOwned, 128);
 #define NARROW(HK, HP) \
     LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_contact_integrate<HK, HP>, blocks, 128, 0, st, a, c.k4, c.prm))
-    if (!c.K && s->narrow_dense) {
-        if (c.contact)
-            LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_dense<true>, blocks, 128, 0, st, a, c.k4, c.prm));
-        else
-            LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_dense<false>, blocks, 128, 0, st, a, c.k4, c.prm));
-    } else if (c.K && c.contact)
+    if (c.K && c.contact)
         NARROW(true, true);
     else if (c.K)
         NARROW(true, false);
@@ -1398,14 +1286,8 @@ bendy_solver *bendy_create(int device) {
         int t = atoi(v);
         if (t >= 32 && t <= 1024 && t % 32 == 0) s->k3_threads = (uint32_t)t;
     }
-    if (const char *v = getenv("BENDY_SCATTER_AGG")) s->scatter_agg = atoi(v) != 0;
     if (const char *v = getenv("BENDY_HALO_OVERLAP")) s->halo_overlap = atoi(v) != 0;
     if (const char *v = getenv("BENDY_SMALL_SCENE")) s->small_scene = atoi(v) != 0;
-    if (const char *v = getenv("BENDY_SCAN_MT")) s->scan_mt = atoi(v) != 0;
-    if (const char *v = getenv("BENDY_NARROW_DENSE")) s->narrow_dense = atoi(v) != 0;
-    if (const char *v = getenv("BENDY_HALO_FUSED")) s->halo_fused = atoi(v) != 0;
-    if (const char *v = getenv("BENDY_SCATTER_ILP")) s->scatter_ilp = atoi(v) != 0;
-    if (const char *v = getenv("BENDY_SORT_FUSED")) s->sort_fused = atoi(v) != 0, s->sort_fused_force = atoi(v) == 2;
     if (const char *v = getenv("BENDY_PDL")) s->pdl = atoi(v);
     if (const char *v = getenv("BENDY_PDL_NCCL")) s->pdl_nccl = atoi(v) != 0;
     // BENDY_SIDE_PRIORITY=1: the circle / polygon branches get the highest stream priority, so their few
@@ -2082,9 +1964,9 @@ int bendy_get_stats(bendy_solver *s, uint64_t *out, int n) {
     OPS;
     if (!out || n < 1) return ops.fail(BENDY_ERR_ARG, "bendy_get_stats: bad arguments");
     for (int k = 0; k < n; k++) out[k] = 0;
-    if (n > 4) out[4] = s->scan_tiles_per_cta;  // 2 / 4: k2_scan_fused_mt is in use (BENDY_SCAN_MT)
-    if (n > 5) out[5] = (s->narrow_dense && !s->has_k) ? 1 : 0;
-    if (n > 6) out[6] = s->sort_fused_capacity;  // != 0: k2_scan_scatter_fused was considered (BENDY_SORT_FUSED)
+    if (n > 4) out[4] = s->n_scan_tiles;
+    if (n > 5) out[5] = s->n_cells;
+    if (n > 6) out[6] = 0;
     if (!s->d_flags.p) return BENDY_OK;
     if (int rc = ops.bind()) return rc;
     int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};

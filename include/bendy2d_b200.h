@@ -180,8 +180,8 @@ int bendy_set_profiling(bendy_solver *s, int profile);
 int bendy_get_kernel_times(bendy_solver *s, double *ms, uint64_t *launches, int n_classes, int reset);
 /* diagnostic counters: out[0] = substeps in which the parallel exact circle pass had to fall back to
  * the plain sequential pass (its path-length bound did not hold), out[1..3] = by cause (path bound,
- * near-list overflow, coordinate scale), out[4] = 2048-cell tiles per CTA of the fused scan (1, or 2 / 4
- * with the opt-in multi-tile scan) */
+ * near-list overflow, coordinate scale), out[4] = scan tiles (2048 cells each) of the broadphase histogram,
+ * out[5] = grid cells */
 int bendy_get_stats(bendy_solver *s, uint64_t *out, int n);
 /* kernels launched (graph nodes included) since creation: the gpu_launches figure of bench.py */
 uint64_t bendy_launch_count(const bendy_solver *s);

@@ -10,8 +10,8 @@ The sources are used as they are, except for four purely syntactic rewrites that
   2. `extern __shared__ T name[];`                  ->  `T *name = (T *)cuemu::dyn_smem();`
   3. `__shared__ T a, b[N];`                        ->  references into per-CTA storage (poisoned at CTA start)
   4. `asm volatile("griddepcontrol...")`            ->  nothing (programmatic dependent launch is a scheduling hint)
-and one semantic hook: the busy-wait of the software grid barrier in k2_scan_fused yields to the fiber
-scheduler (a cooperative scheduler never pre-empts a spinning thread).
+(The kernels no longer contain a software grid barrier; a busy-wait would have to yield to the fiber scheduler
+through BENDY_SPIN_HOOK: a cooperative scheduler never pre-empts a spinning thread.)
 """
 from __future__ import annotations
 
@@ -31,7 +31,6 @@ _LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)\s*<<<(.+?)>>>\s*\(", re.S)
 _EXTERN_SHARED = re.compile(r"extern\s+__shared__\s+([\w ]+?)\s+(\w+)\s*\[\s*\]\s*;")
 _SHARED = re.compile(r"^(\s*)__shared__\s+((?:unsigned\s+|volatile\s+)*\w+)\s+([^;\n]+);", re.M)
 _ASM = re.compile(r'asm\s+volatile\s*\(\s*"griddepcontrol[^"]*"[^;]*;')
-_SPIN = re.compile(r"while\s*\(\*\(volatile uint32_t \*\)barrier < gridDim\.x\)\s*\{\s*\}")
 
 
 def transform(text: str, name: str) -> str:
@@ -63,7 +62,6 @@ def transform(text: str, name: str) -> str:
     text = _SHARED.sub(shared, text)
     text, n_launch = _LAUNCH.subn(launch, text)
     text = _ASM.sub(";", text)
-    text, n_spin = _SPIN.subn("while (*(volatile uint32_t *)barrier < gridDim.x) { cuemu::yield_spin(); }", text)
 
     if any("<<<" in ln and not ln.lstrip().startswith("//") for ln in text.splitlines()):
         raise SystemExit(f"cuemu/build.py: an unconverted <<< >>> launch is left in {name}")
@@ -71,8 +69,6 @@ def transform(text: str, name: str) -> str:
         left = [ln for ln in text.splitlines() if "__shared__" in ln and not ln.lstrip().startswith("//")]
         if left:
             raise SystemExit(f"cuemu/build.py: unconverted __shared__ in {name}: {left[0].strip()}")
-    if name == "kernels.cuh" and n_spin < 1:
-        raise SystemExit("cuemu/build.py: no grid-barrier spin loop (k2_scan_fused*) was found (kernel changed?)")
     return text
 
 

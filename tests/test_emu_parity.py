@@ -83,9 +83,9 @@ def test_parity_suite_on_emulator(emu_lib):
 
 
 def test_parity_suite_on_emulator_plain_launches(emu_lib):
-    """same kernels without the small-scene single launch and without the fused scan"""
+    """same kernels without the small-scene single launch and without programmatic dependent launch"""
     run_gpu_tests_on_emulator(emu_lib, ["tests/test_gpu_parity.py", "-k", "c1_reference or c2_small or c3_small or c4_small"],
-                              extra_env={"BENDY_SMALL_SCENE": "0", "BENDY_SCAN_FUSED": "0", "BENDY_PDL": "0"})
+                              extra_env={"BENDY_SMALL_SCENE": "0", "BENDY_PDL": "0"})
 
 
 @pytest.mark.parametrize("order", ["2"])
@@ -93,7 +93,7 @@ def test_results_do_not_depend_on_the_thread_schedule(emu_lib, order):
     """A device promises no execution order.  The emulation resumes runnable threads last-first (1) or in a new
     pseudo-random order every sweep (2): every bit-exact parity test must still pass, i.e. slot orders, atomic
     arrival orders and near-list orders never leak into results."""
-    run_gpu_tests_on_emulator(emu_lib, ["tests/test_gpu_parity.py", "tests/test_z_gpu_variants.py", "tests/test_golden.py",
+    run_gpu_tests_on_emulator(emu_lib, ["tests/test_gpu_parity.py", "tests/test_z_gpu_switches.py", "tests/test_golden.py",
                                         "tests/test_z_gpu_strips_replicated.py", "-k", "not full_size"],
                               extra_env={"CUEMU_ORDER": order})
 
@@ -103,9 +103,9 @@ def test_limits_strips_snapshot_golden_on_emulator(emu_lib):
                                         "tests/test_golden.py", "tests/test_z_gpu_strips_replicated.py", "-k", "not 4200 and not nccl"])
 
 
-def test_opt_in_variants_on_emulator(emu_lib):
-    """the switches that are OFF by default (tests/test_z_gpu_variants.py): bit-identical to the default path"""
-    run_gpu_tests_on_emulator(emu_lib, ["tests/test_z_gpu_variants.py"])
+def test_scan_shapes_and_switches_on_emulator(emu_lib):
+    """tests/test_z_gpu_switches.py: the one-pass scan over grid shapes, scheduling switches"""
+    run_gpu_tests_on_emulator(emu_lib, ["tests/test_z_gpu_switches.py"])
 
 
 def test_randomised_worlds_on_emulator(emu_lib):

@@ -1,0 +1,116 @@
+"""The one-pass histogram scan (scan-tile totals accumulated per CTA next to the histogram) over grid shapes from
+one scan tile to hundreds, including discs spread over so many cell rows that a CTA's totals leave its
+shared-memory table; and the environment switches of libbendy2d_b200 that change scheduling, never results
+(BENDY_PDL levels, BENDY_K3_THREADS, BENDY_SMALL_SCENE): bit-identical to the default and to the oracle.
+
+(Round 1's opt-in kernel variants - multi-tile fused scan, fused scan+scatter, 4-discs-per-thread scatter,
+warp-aggregated scatter, lane-dense narrowphase, fused halo receive - were proven bit-identical on the device in
+round 2 and measured: none was faster (profiles/r2_variants_ab_result.txt), so they were removed.)"""
+import os
+
+import numpy as np
+import pytest
+
+from bendy2d_b200 import Solver, scenes
+from helpers import bits, compare_state, f32, oracle_from_scene, sync_schedule
+
+pytestmark = pytest.mark.gpu
+
+
+class env:
+    """environment switches are read by bendy_create"""
+
+    def __init__(self, **kv):
+        self.kv, self.old = kv, {}
+
+    def __enter__(self):
+        for k, v in self.kv.items():
+            self.old[k] = os.environ.get(k)
+            os.environ[k] = str(v)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def run(sc, n_updates, grid_cell=0.0, **switches):
+    with env(**switches):
+        g = Solver()
+    sc.load_into(g)
+    if grid_cell:
+        g.set_grid_cell(grid_cell)
+    for _ in range(n_updates):
+        g.update(sc.dt)
+    return g
+
+
+def same_bits(a, b):
+    for x, y in zip(a.read_particles(), b.read_particles()):
+        assert np.array_equal(bits(x), bits(y))
+    if a.get_circles_len():
+        for x, y in zip(a.read_circles()[:2], b.read_circles()[:2]):
+            assert np.array_equal(bits(x), bits(y))
+
+
+@pytest.mark.parametrize("width,height,cell", [(40.0, 16.0, 0.24), (64.0, 40.0, 0.24), (128.0, 64.0, 0.24), (700.0, 400.0, 0.21)])
+def test_one_pass_scan_over_grid_shapes(width, height, cell):
+    """1 / 22 / 70 / 3100 scan tiles of 2048 cells: piled discs against the oracle"""
+    sc = scenes.c2_free_particles(60, 40)
+    sc.bounds = (0.0, 0.0, float(width), float(height))
+    g = Solver()
+    sc.load_into(g)
+    g.set_grid_cell(cell)
+    o = oracle_from_scene(sc)
+    sync_schedule(g, o, sc)
+    for k in range(3):
+        g.update(sc.dt, n=20)
+        for _ in range(20):
+            o.update(sc.dt)
+        st = compare_state(g, o, max(width, height), 1e-5, f"grid {width}x{height}/{cell} after {20 * (k + 1)}")
+        assert st["ulp_pos"] == 0 and st["ulp_prev"] == 0, st
+    assert g.stats()["scan_tiles"] == -(-(int(np.ceil(width / cell)) * int(np.ceil(height / cell)) + 1) // 2048)
+
+
+def test_discs_spread_over_hundreds_of_scan_tiles_per_cta():
+    """consecutive discs 4 units apart vertically: one CTA's 256 discs cover ~180 scan tiles (its table holds 32),
+    the rest go to the global totals directly; linked pairs so that there are contacts to find"""
+    n = 600
+    base = np.stack([np.full(n, 20.0), 5.0 + 4.0 * np.arange(n)], 1)
+    pos = np.concatenate([base, base + np.array([0.15, 0.0])]).astype(f32)  # every site: two overlapping discs
+    sc = scenes.Scene(name="column", particles=pos, bounds=(0.0, 0.0, 64.0, 2500.0), particle_radius=0.1)
+    # the upper half of the pairs is linked (link partitions), the lower half is free (chunk CTAs of k2_count)
+    ab = np.stack([np.arange(n // 2), n + np.arange(n // 2)], 1).astype(np.uint32)
+    sc.links_ab, sc.links_len = ab, np.full(len(ab), 0.25, f32)
+    g = Solver()
+    sc.load_into(g)
+    g.set_grid_cell(0.42)  # 153 x 5953 cells: 445 scan tiles, a disc site every 9.5 cell rows
+    o = oracle_from_scene(sc)
+    sync_schedule(g, o, sc)
+    for k in range(10):
+        g.update(sc.dt)
+        o.update(sc.dt)
+    assert g.stats()["scan_tiles"] > 400
+    st = compare_state(g, o, 2500.0, 1e-5, "column")
+    assert st["ulp_pos"] == 0 and st["ulp_prev"] == 0, st
+    p, _ = g.read_particles()
+    assert (np.abs(p[:n, 0] - p[n:, 0]) > 0.16).all(), "the pairs were pushed apart: the contacts were found"
+
+
+@pytest.mark.parametrize("switches", [{"BENDY_PDL": 0}, {"BENDY_PDL": 1}, {"BENDY_PDL": 2}, {"BENDY_K3_THREADS": 256},
+                                      {"BENDY_K3_THREADS": 64}])
+def test_scheduling_switches_do_not_change_results(switches):
+    sc = scenes.c3_softbody_field(4, 3, 3, 4)
+    ref = run(sc, 40)
+    alt = run(sc, 40, **switches)
+    same_bits(ref, alt)
+
+
+def test_small_scene_single_launch_equals_multi_kernel_path():
+    sc = scenes.c1_softbody_blob()
+    a = run(sc, 30)
+    b = run(sc, 30, BENDY_SMALL_SCENE=0)
+    same_bits(a, b)
+    assert a.launch_count() < b.launch_count()
