@@ -175,7 +175,7 @@ struct bendy_solver {
     int pdl = 3;                // BENDY_PDL: 0 = off, 1 = programmatic dependent launch for links/scan/scatter,
                                 // 2 = + narrowphase, 3 = + the circle / polygon branches (default); not yet used
                                 // on the NCCL strip path (BENDY_PDL_NCCL=1)
-    bool pdl_nccl = false;
+    bool pdl_nccl = true;   // BENDY_PDL_NCCL=0 turns programmatic dependent launch off on the strip path
     DevBuf<float2> d_sorted_pos;
     DevBuf<uint32_t> d_circ_tile_count, d_circ_tile_ids;
     uint32_t n_scan_tiles = 0, n_circ_tiles = 0;
@@ -638,11 +638,13 @@ int Ops::grid_for(float bx, float by, float bw, float bh, StepParams *p, uint32_
     if (s->win_x1 > bx && s->win_x1 < bx + (float)wx) wx = (double)(s->win_x1 - bx);
     float h = s->grid_cell;
     if (!(h > 0.f)) {
-        // auto: about two cells per particle (the per-cell scan traffic then stays below the per-disc
-        // traffic), never below the contact distance 2*r_p
-        // and, so that a disc's partners lie in a 2x2 block of cells, at least 4.2*r_p
+        // auto: 4.2*r_p, so that a disc's partners lie in a 2x2 block of cells with as few bystanders as possible;
+        // larger only when that would be more than about eight cells per particle (a sparse world: the per-cell
+        // scan traffic would exceed the per-disc traffic).  Measured on strips: the end ranks' windows reach the
+        // world's walls, and with the former two cells per particle their cells grew to 0.9 (4.7x the candidates
+        // per disc, narrowphase 130 instead of 56 us for 2M discs).
         double np = std::max<double>(s->p_pos.size(), 1.0);
-        h = std::max((float)std::sqrt(wx * wy / (2.0 * np)), 4.2f * s->particle_radius);
+        h = std::max((float)std::sqrt(wx * wy / (8.0 * np)), 4.2f * s->particle_radius);
     }
     if (h < 2.0f * s->particle_radius) h = 2.0f * s->particle_radius;
     if (!(h > 0.f)) h = 1.0f;

@@ -195,9 +195,16 @@ def _load_part(part: StripPart, device: int, replicated=None) -> Solver:
     if part.world > 1:
         sv._ck(sv._L.bendy_halo_configure(sv._h, part.ghost_cap, part.send_left_below, part.send_right_above,
                                           part.stray_left, part.stray_right))
-        # cells only where owned discs (up to the stray limit) and ghosts (one band beyond the edge) can be
-        x0 = part.x_left - 1.5 * part.band if np.isfinite(part.x_left) else -3.0e38
-        x1 = part.x_right + 1.5 * part.band if np.isfinite(part.x_right) else 3.0e38
+        # cells only where owned discs (up to the stray limit) and ghosts (one band beyond the edge) can be.  The
+        # end strips have no edge on their open side: there the window ends 1.5 bands beyond the owned discs (a disc
+        # that leaves the window is clamped into the border cells, which stays correct) - a window up to the world's
+        # wall made the end ranks scan several times the cells of the interior ranks (measured: +25 us per substep)
+        px = part.scene.particles[:, 0]
+        px = px[np.isfinite(px)]
+        lo = float(px.min()) if len(px) else 0.0
+        hi = float(px.max()) if len(px) else 0.0
+        x0 = part.x_left - 1.5 * part.band if np.isfinite(part.x_left) else lo - 1.5 * part.band
+        x1 = part.x_right + 1.5 * part.band if np.isfinite(part.x_right) else hi + 1.5 * part.band
         sv._ck(sv._L.bendy_set_grid_window(sv._h, x0, x1))
     return sv
 
