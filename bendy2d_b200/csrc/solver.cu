@@ -169,6 +169,7 @@ struct bendy_solver {
     bool has_k = false;
     // grid
     DevBuf<uint32_t> d_cell_count, d_cell_start, d_tile_sum, d_sorted_id, d_slot_of;
+    bool poly_fused = true;     // BENDY_POLY_FUSED=0: the multi-launch polygon chain also for <= 1024 polygons
     uint32_t k3_threads = 128;  // BENDY_K3_THREADS
     bool halo_overlap = false;  // BENDY_HALO_OVERLAP
     bool small_scene = true;    // BENDY_SMALL_SCENE=0 forces the multi-kernel path for tiny scenes
@@ -584,9 +585,10 @@ int Ops::rebuild() {
         CK(cudaMemsetAsync(s->d_poly_first_row.p, 0xFF, sizeof(uint32_t), s->stream));
     }
     if (!s->d_flags.p) {
-        CK(s->d_flags.ensure(8));  // [0] error flags, [1..4] circle-pass fallbacks (statistics)
+        CK(s->d_flags.ensure(8));  // [0] error flags, [1..4] circle-pass fallbacks (statistics), [5] polygon tiles built
         CK(cudaMemsetAsync(s->d_flags.p, 0, 8 * sizeof(int), s->stream));
     }
+    CK(cudaMemsetAsync(s->d_flags.p + 5, 0, sizeof(int), s->stream));  // the polygon tiles are rebuilt from scratch
     CK(s->d_prm.ensure(1));
     if (!s->h_prm_ring) {
         CK(cudaHostAlloc(&s->h_prm_ring, sizeof(StepParams) * bendy_solver::kPrmRing, cudaHostAllocDefault));
@@ -639,12 +641,12 @@ int Ops::grid_for(float bx, float by, float bw, float bh, StepParams *p, uint32_
     float h = s->grid_cell;
     if (!(h > 0.f)) {
         // auto: 4.2*r_p, so that a disc's partners lie in a 2x2 block of cells with as few bystanders as possible;
-        // larger only when that would be more than about eight cells per particle (a sparse world: the per-cell
+        // larger only when that would be more than about four cells per particle (a sparse world: the per-cell
         // scan traffic would exceed the per-disc traffic).  Measured on strips: the end ranks' windows reach the
         // world's walls, and with the former two cells per particle their cells grew to 0.9 (4.7x the candidates
         // per disc, narrowphase 130 instead of 56 us for 2M discs).
         double np = std::max<double>(s->p_pos.size(), 1.0);
-        h = std::max((float)std::sqrt(wx * wy / (8.0 * np)), 4.2f * s->particle_radius);
+        h = std::max((float)std::sqrt(wx * wy / (4.0 * np)), 4.2f * s->particle_radius);
     }
     if (h < 2.0f * s->particle_radius) h = 2.0f * s->particle_radius;
     if (!(h > 0.f)) h = 1.0f;
@@ -723,6 +725,11 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
             CK(s->d_poly_tiles.ensure((size_t)ptiles * (BENDY_POLY_CAP + 1)));
         }
     }
+    // the fused polygon chain only rebuilds its tile lists when an AABB moved: a new tile geometry invalidates them
+    if (poly_tiles && s->d_flags.p &&
+        (!s->prm_valid || p.pox != s->prm.pox || p.poy != s->prm.poy || p.pinv != s->prm.pinv || p.pnx != s->prm.pnx ||
+         p.pny != s->prm.pny))
+        CK(cudaMemsetAsync(s->d_flags.p + 5, 0, sizeof(int), s->stream));
     s->prm = p;
     s->prm_valid = true;
     // stage through a pinned ring so the async copy never reads a host value that changed later
@@ -889,10 +896,17 @@ int Ops::launch_polygon_chain(const SubstepCtx &c) {
     PolyArgs pa{pts,          s->d_poly_start.p, s->d_poly_static.p, c.nPoly, s->d_poly_center.p, s->d_poly_box.p,
                 s->d_poly_tiles.p, s->d_flags.p,      s->d_poly_first_row.p};
     const bool bins = c.contact || c.nPoly >= 2;
+    PolyLinkArgs la{s->d_poly_link_start.p, s->d_poly_link_ab.p, s->d_poly_link_len.p};
+    if (c.nPoly <= 1024 && s->poly_fused) {
+        // up to 1024 polygons: the whole chain in one launch of one CTA; the tiles are only rebuilt when an AABB moved
+        const uint32_t threads = c.nPoly <= 128 ? 128 : (c.nPoly <= 256 ? 256 : (c.nPoly <= 512 ? 512 : 1024));
+        LAUNCH(BENDY_K_POLY_PREP, launch_k(c.pdl > 2, k_polygons_fused, 1, threads, 0, c.qg, pts, pa, la, c.prm, s->n_poly_tiles,
+                                           bins ? 1 : 0, s->d_flags.p + 5));
+        return BENDY_OK;
+    }
     if (bins)
         LAUNCH(BENDY_K_POLY_PREP, cudaMemsetAsync(s->d_poly_tiles.p, 0,
                                                   (size_t)s->n_poly_tiles * (BENDY_POLY_CAP + 1) * sizeof(uint32_t), c.qg));
-    PolyLinkArgs la{s->d_poly_link_start.p, s->d_poly_link_ab.p, s->d_poly_link_len.p};
     LAUNCH(BENDY_K_POLY_PREP, k_poly_prepare<<<cdiv(c.nPoly, 128), 128, 0, c.qg>>>(pts, pa, la, c.prm, bins ? 1 : 0));
     if (c.nPoly >= 2) {
         LAUNCH(BENDY_K_POLY_CONTACT, launch_k(c.pdl > 2, k4_poly_pair_prescan, cdiv(c.nPoly, 128), 128, 0, c.qg, pa, c.prm));
@@ -1290,6 +1304,7 @@ bendy_solver *bendy_create(int device) {
     }
     if (const char *v = getenv("BENDY_HALO_OVERLAP")) s->halo_overlap = atoi(v) != 0;
     if (const char *v = getenv("BENDY_SMALL_SCENE")) s->small_scene = atoi(v) != 0;
+    if (const char *v = getenv("BENDY_POLY_FUSED")) s->poly_fused = atoi(v) != 0;
     if (const char *v = getenv("BENDY_PDL")) s->pdl = atoi(v);
     if (const char *v = getenv("BENDY_PDL_NCCL")) s->pdl_nccl = atoi(v) != 0;
     // BENDY_SIDE_PRIORITY=1: the circle / polygon branches get the highest stream priority, so their few
