@@ -522,7 +522,7 @@ int Ops::rebuild() {
     for (uint32_t i = s->N; i < s->Npad; i++) pos[i] = prev[i] = make_float2(0.f, 0.f);
     CK(upload(s->d_pos, pos, s->stream));
     CK(upload(s->d_prev, prev, s->stream));
-    CK(s->d_stage.ensure(std::max<size_t>(s->Npad, 1)));
+    CK(s->d_stage.ensure(2 * std::max<size_t>(s->Npad, 1)));  // pos | prev halves of the host <-> device staging
     s->accel_pending = false;
     if (s->any_acc) {
         std::vector<float2> acc(s->Npad, make_float2(0.f, 0.f));
@@ -1708,15 +1708,16 @@ int bendy_read_particles(bendy_solver *s, size_t first, size_t n, float *pos_xy,
     // device is authoritative: gather USER order on the device, copy straight into the caller's buffers
     if (int rc = ops.ensure_ready()) return rc;
     if (int rc = ops.flush_events()) return rc;
-    for (int which = 0; which < 2; which++) {
-        float *out = which == 0 ? pos_xy : prev_xy;
-        if (!out) continue;
-        const float2 *src = which == 0 ? s->d_pos.p : s->d_prev.p;
-        k_gather<<<cdiv((uint32_t)n, 256), 256, 0, s->stream>>>(src, s->d_rank.p + first, (uint32_t)n, s->d_stage.p);
+    // one gather launch for both arrays into the two halves of the staging buffer, two copies, ONE synchronise
+    // (check_flags reads its word with the same synchronise)
+    if (pos_xy || prev_xy) {
+        float2 *st0 = s->d_stage.p, *st1 = s->d_stage.p + s->Npad;
+        k_gather2<<<cdiv((uint32_t)n, 256), 256, 0, s->stream>>>(pos_xy ? s->d_pos.p : nullptr, prev_xy ? s->d_prev.p : nullptr,
+                                                                  s->d_rank.p + first, (uint32_t)n, st0, st1);
         s->launches++;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(out, s->d_stage.p, n * sizeof(float2), cudaMemcpyDeviceToHost, s->stream));
-        CK(cudaStreamSynchronize(s->stream));
+        if (pos_xy) CK(cudaMemcpyAsync(pos_xy, st0, n * sizeof(float2), cudaMemcpyDeviceToHost, s->stream));
+        if (prev_xy) CK(cudaMemcpyAsync(prev_xy, st1, n * sizeof(float2), cudaMemcpyDeviceToHost, s->stream));
     }
     return ops.check_flags();
 }
@@ -1734,15 +1735,15 @@ int bendy_write_particles(bendy_solver *s, size_t first, size_t n, const float *
         return BENDY_OK;
     }
     if (int rc = ops.ensure_ready()) return rc;
-    for (int which = 0; which < 2; which++) {
-        const float *in = which == 0 ? pos_xy : prev_xy;
-        if (!in) continue;
-        float2 *dst = which == 0 ? s->d_pos.p : s->d_prev.p;
-        CK(cudaMemcpyAsync(s->d_stage.p, in, n * sizeof(float2), cudaMemcpyHostToDevice, s->stream));
-        k_scatter<<<cdiv((uint32_t)n, 256), 256, 0, s->stream>>>(s->d_stage.p, s->d_rank.p + first, (uint32_t)n, dst);
+    if (pos_xy || prev_xy) {
+        float2 *st0 = s->d_stage.p, *st1 = s->d_stage.p + s->Npad;
+        if (pos_xy) CK(cudaMemcpyAsync(st0, pos_xy, n * sizeof(float2), cudaMemcpyHostToDevice, s->stream));
+        if (prev_xy) CK(cudaMemcpyAsync(st1, prev_xy, n * sizeof(float2), cudaMemcpyHostToDevice, s->stream));
+        k_scatter2<<<cdiv((uint32_t)n, 256), 256, 0, s->stream>>>(pos_xy ? st0 : nullptr, prev_xy ? st1 : nullptr,
+                                                                   s->d_rank.p + first, (uint32_t)n, s->d_pos.p, s->d_prev.p);
         s->launches++;
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(s->stream));  // the caller's buffer may be reused after return
+        CK(cudaStreamSynchronize(s->stream));  // the caller's buffers may be reused after return
     }
     s->host_valid = false;
     return BENDY_OK;
