@@ -107,6 +107,7 @@ def signatures():
         "bendy_get_device_buffers": (i, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]),
         "bendy_halo_configure": (i, [vp, u32, fl, fl, fl, fl]),
         "bendy_set_grid_window": (i, [vp, fl, fl]),
+        "bendy_strip_set_cross_links": (i, [vp, sz, u32p, u32p, C.POINTER(C.c_uint8), f32p, u32, u32p, sz, u32p, sz, u32p, sz, sz]),
         "bendy_nccl_unique_id": (i, [vp]),
         "bendy_halo_comm_nccl": (i, [vp, vp, i, i]),
         "bendy_halo_connect_local": (i, [vp, vp]),

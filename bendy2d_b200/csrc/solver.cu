@@ -206,6 +206,19 @@ struct bendy_solver {
     ncclComm_t nccl_comm = nullptr;
     int comm_rank = -1, comm_world = 0;
     bendy_solver *peer[2] = {nullptr, nullptr};  // same-process transport (1-GPU emulation of strips)
+    // links that cross a strip edge (cut bodies): host tables in USER particle indices, device tables in internal ones
+    struct XlHost {
+        uint32_t mine, slot;
+        float len;
+        uint32_t i_am_a;
+    };
+    std::vector<XlHost> xl;                  // sorted by colour
+    std::vector<uint32_t> xl_colour_start;   // n_colours + 1
+    std::vector<uint32_t> xl_send[2];        // my endpoints the left / right neighbour needs (user indices, agreed order)
+    uint32_t xl_recv[2] = {0, 0};            // endpoints I receive from the left / right neighbour
+    DevBuf<CrossLink> d_xl;
+    DevBuf<uint32_t> d_xl_send_idx;          // [left block | right block] internal indices
+    DevBuf<float2> d_xl_sendbuf, d_xl_ghost; // [left block | right block]
     cudaEvent_t ev_phase_a = nullptr, ev_xchg = nullptr;
 
     // ---------------- per-update params
@@ -291,6 +304,7 @@ struct Ops {  // helper with access to the solver; keeps bendy_solver a plain st
     SubstepCtx make_ctx();
     int launch_links_local(const SubstepCtx &c, cudaStream_t q, uint32_t p0, uint32_t p1, int halo_mode);
     int launch_links_global(const SubstepCtx &c, cudaStream_t q);
+    int launch_links_cross(const SubstepCtx &c);
     int launch_polygon_chain(const SubstepCtx &c);
     int launch_circle_chain(SubstepCtx &c);
     int launch_count_unlinked(const SubstepCtx &c);
@@ -554,6 +568,18 @@ int Ops::rebuild() {
         CK(upload(s->d_poly_link_len, s->gl_len, s->stream));
     }
     CK(upload(s->d_clinks, s->cl, s->stream));
+    if (!s->xl.empty()) {  // links across strip edges: user -> internal indices
+        std::vector<CrossLink> x(s->xl.size());
+        for (size_t k = 0; k < x.size(); k++)
+            x[k] = CrossLink{s->plan_p.rank[s->xl[k].mine], s->xl[k].slot, s->xl[k].len, s->xl[k].i_am_a};
+        CK(upload(s->d_xl, x, s->stream));
+        std::vector<uint32_t> idx;
+        for (int side = 0; side < 2; side++)
+            for (uint32_t u : s->xl_send[side]) idx.push_back(s->plan_p.rank[u]);
+        CK(upload(s->d_xl_send_idx, idx, s->stream));
+        CK(s->d_xl_sendbuf.ensure(std::max<size_t>(idx.size(), 1)));
+        CK(s->d_xl_ghost.ensure(std::max<size_t>((size_t)s->xl_recv[0] + s->xl_recv[1], 1)));
+    }
     // ---- polygons
     {
         std::vector<uint32_t> pstart(s->polys.size() + 1, 0);
@@ -833,7 +859,9 @@ SubstepCtx Ops::make_ctx() {
                        c.halo ? s->ghost_cap : 0u};
     const LinkPlan &P = s->plan_p;
     c.n_in_parts = P.n_parts() ? P.part_start.back() : 0u;
-    c.fuse_count = c.discs && P.n_global_colours() == 0 && c.n_in_parts > 0;
+    // the histogram (and the halo packing) must see the positions after ALL links: global colours and links that
+    // cross a strip edge run behind the partition kernel
+    c.fuse_count = c.discs && P.n_global_colours() == 0 && c.n_in_parts > 0 && s->xl.empty();
     c.k1 = K1Args{c.pos, s->d_prev.p, c.acc ? s->d_accel.p : nullptr, c.dk, s->d_crad.p, s->d_gstatic.p, s->nP, s->nC, s->N};
     c.k4 = K4Args{c.pos + s->nP + s->nC, s->d_poly_start.p, s->d_poly_center.p, s->d_poly_box.p, s->d_poly_tiles.p,
                   s->d_poly_static.p};
@@ -991,7 +1019,52 @@ int Ops::launch_particle_links(const SubstepCtx &c, int phase, bool *ghosts_done
     }
     if (int rc = launch_links_local(c, c.st, 0, n_parts, c.halo ? 1 : 0)) return rc;
     if (int rc = launch_links_global(c, c.st)) return rc;
+    if (int rc = launch_links_cross(c)) return rc;
     return launch_count_unlinked(c);
+}
+
+// Links across strip edges, as trailing colours behind all local and global links of every strip.  Before each
+// colour the ranks exchange the current positions of the endpoints the neighbour needs (ncclSend/Recv inside the
+// captured graph; a few KB), then each rank relaxes its links of that colour and keeps its own endpoints' halves.
+// The sequential order this equals: [strip 0's schedule][strip 1's] ... [cross colour 0][cross colour 1] ...
+int Ops::launch_links_cross(const SubstepCtx &c) {
+    if (s->xl.empty()) return BENDY_OK;
+    if (!s->nccl_comm)
+        return fail(BENDY_ERR_UNSUPPORTED, "links across strip edges need the NCCL transport (bendy_halo_comm_nccl); the "
+                                           "same-process strip group does not carry them");
+    auto ck = [&](ncclResult_t r, const char *what) -> int {
+        if (r == ncclSuccess) return BENDY_OK;
+        s->sticky = BENDY_ERR_CUDA;
+        return fail(BENDY_ERR_CUDA, std::string("NCCL error in ") + what + ": " + g_nccl.GetErrorString(r));
+    };
+    const uint32_t ns[2] = {(uint32_t)s->xl_send[0].size(), (uint32_t)s->xl_send[1].size()};
+    const uint32_t n_send = ns[0] + ns[1];
+    const int nb[2] = {s->comm_rank - 1, s->comm_rank + 1};
+    const uint32_t n_colours = (uint32_t)s->xl_colour_start.size() - 1;
+    for (uint32_t col = 0; col < n_colours; col++) {
+        const uint32_t l0 = s->xl_colour_start[col], l1 = s->xl_colour_start[col + 1];
+        if (n_send)
+            LAUNCH(BENDY_K_LINKS_GLOBAL,
+                   k_xl_pack<<<cdiv(n_send, 256), 256, 0, c.st>>>(c.pos, s->d_xl_send_idx.p, n_send, s->d_xl_sendbuf.p));
+        if (int rc = ck(g_nccl.GroupStart(), "ncclGroupStart")) return rc;
+        for (int side = 0; side < 2; side++) {
+            float2 *sb = s->d_xl_sendbuf.p + (side ? ns[0] : 0u), *gb = s->d_xl_ghost.p + (side ? s->xl_recv[0] : 0u);
+            if (ns[side])
+                if (int rc = ck(g_nccl.Send(sb, 2 * (size_t)ns[side], ncclFloat, nb[side], s->nccl_comm, c.st), "ncclSend")) return rc;
+            if (s->xl_recv[side])
+                if (int rc = ck(g_nccl.Recv(gb, 2 * (size_t)s->xl_recv[side], ncclFloat, nb[side], s->nccl_comm, c.st), "ncclRecv"))
+                    return rc;
+        }
+        if (int rc = ck(g_nccl.GroupEnd(), "ncclGroupEnd")) return rc;
+        if (s->capturing)
+            s->count_in_capture++;
+        else
+            s->launches++, s->k_launches[BENDY_K_HALO]++;
+        if (l1 > l0)
+            LAUNCH(BENDY_K_LINKS_GLOBAL,
+                   k_xl_links<<<cdiv(l1 - l0, 256), 256, 0, c.st>>>(c.pos, s->d_xl_ghost.p, s->d_xl.p, l0, l1));
+    }
+    return BENDY_OK;
 }
 
 // K2 grid build: exclusive scan of the cell histogram (one pass: the scan-tile totals came with the histogram),
@@ -2083,6 +2156,40 @@ int bendy_halo_comm_nccl(bendy_solver *s, const void *unique_id128, int rank, in
     if (r != ncclSuccess) return ops.fail(BENDY_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
     s->comm_rank = rank, s->comm_world = world;
     ops.drop_graph();
+    return BENDY_OK;
+}
+
+int bendy_strip_set_cross_links(bendy_solver *s, size_t n, const uint32_t *mine, const uint32_t *slot, const uint8_t *i_am_a,
+                                const float *len, uint32_t n_colours, const uint32_t *colour_start, size_t n_send_left,
+                                const uint32_t *send_left, size_t n_send_right, const uint32_t *send_right,
+                                size_t n_recv_left, size_t n_recv_right) {
+    NEED(s);
+    OPS;
+    if (n && (!mine || !slot || !i_am_a || !len || !colour_start || n_colours == 0))
+        return ops.fail(BENDY_ERR_ARG, "bendy_strip_set_cross_links: null table");
+    if ((n_send_left && !send_left) || (n_send_right && !send_right))
+        return ops.fail(BENDY_ERR_ARG, "bendy_strip_set_cross_links: null send list");
+    if (n_recv_left + n_recv_right > 0x7FFFFFFFu || n > 0x7FFFFFFFu) return ops.fail(BENDY_ERR_ARG, "too many cross links");
+    if (n && (colour_start[0] != 0 || colour_start[n_colours] != n))
+        return ops.fail(BENDY_ERR_ARG, "bendy_strip_set_cross_links: colour_start must run from 0 to n");
+    const size_t np = s->p_pos.size();
+    for (size_t k = 0; k < n; k++)
+        if (mine[k] >= np || slot[k] >= n_recv_left + n_recv_right)
+            return ops.fail(BENDY_ERR_LINK, "bendy_strip_set_cross_links: endpoint or ghost slot out of range");
+    for (uint32_t c = 0; c < n_colours && n; c++)
+        if (colour_start[c] > colour_start[c + 1]) return ops.fail(BENDY_ERR_ARG, "colour_start must be non-decreasing");
+    for (size_t k = 0; k < n_send_left; k++)
+        if (send_left[k] >= np) return ops.fail(BENDY_ERR_LINK, "bendy_strip_set_cross_links: send index out of range");
+    for (size_t k = 0; k < n_send_right; k++)
+        if (send_right[k] >= np) return ops.fail(BENDY_ERR_LINK, "bendy_strip_set_cross_links: send index out of range");
+    if (int rc = edit_begin(s)) return rc;
+    s->xl.resize(n);
+    for (size_t k = 0; k < n; k++) s->xl[k] = bendy_solver::XlHost{mine[k], slot[k], len[k], i_am_a[k] ? 1u : 0u};
+    s->xl_colour_start.assign(n ? colour_start : nullptr, n ? colour_start + n_colours + 1 : nullptr);
+    s->xl_send[0].assign(send_left, send_left + n_send_left);
+    s->xl_send[1].assign(send_right, send_right + n_send_right);
+    s->xl_recv[0] = (uint32_t)n_recv_left, s->xl_recv[1] = (uint32_t)n_recv_right;
+    edit_end(s);
     return BENDY_OK;
 }
 

@@ -57,6 +57,9 @@ class StripPart:
     ghost_cap: int
     stray_margin_left: Optional[float] = None   # how far an owned disc may sit inside the left / right neighbour
     stray_margin_right: Optional[float] = None  # before the ownership counts as stale (None = band / 2)
+    cross: Optional[dict] = None                # links across the strip's edges (cut bodies): tables for
+                                                # bendy_strip_set_cross_links + "global_links" (scene link indices)
+    local_links: Optional[np.ndarray] = None    # scene link index of every link of the local scene
 
     @property
     def send_left_below(self) -> float:   # owned discs with x below this go to the left neighbour
@@ -80,15 +83,37 @@ class StripPart:
         return float(self.x_right + m) if np.isfinite(self.x_right) else float("inf")
 
 
+def cross_link_colours(ab: np.ndarray) -> np.ndarray:
+    """Greedy colouring of the links across strip edges, in scene order (deterministic: every rank computes the
+    same colours from the same scene): links of one colour share no particle."""
+    used = {}
+    colour = np.empty(len(ab), np.int64)
+    for k, (a, b) in enumerate(ab.tolist()):
+        ua, ub = used.setdefault(a, set()), used.setdefault(b, set())
+        c = 0
+        while c in ua or c in ub:
+            c += 1
+        ua.add(c), ub.add(c)
+        colour[k] = c
+    return colour
+
+
 def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodies: Optional[np.ndarray] = None,
-                    cap_factor: float = 2.0) -> List[StripPart]:
+                    cap_factor: float = 2.0, cut_bodies: bool = False) -> List[StripPart]:
     """Split `scene` into `world` strips.  Polygons and Circles are replicated: every strip carries all of them.
     Nothing a particle does reaches a polygon, so the copies evolve identically; the corrections a strip's own
     discs collect for a Circle are summed over all strips by the library (integer all-reduce) before they are
-    applied, so the Circles' copies stay identical too."""
+    applied, so the Circles' copies stay identical too.
+
+    cut_bodies=False: whole bodies (link components) go to the strip of their centroid; no link crosses an edge.
+    cut_bodies=True: every particle goes to the strip of its own x (equal particle counts); links whose ends lie in
+    neighbouring strips become CROSS links, relaxed after all the strips' own links in colours of their own, the
+    endpoint positions exchanged before every colour (bendy_strip_set_cross_links).  For bodies wider than a strip."""
 
     n = scene.n_particles
-    if bodies is None:
+    if cut_bodies:
+        bodies = np.arange(n, dtype=np.int64)  # every particle is its own "body" for the geometry of the cut
+    elif bodies is None:
         bodies = scene.body_of if scene.body_of is not None else body_ids(scene)
     bodies = np.asarray(bodies, np.int64)
     nb = int(bodies.max()) + 1 if n else 0
@@ -134,15 +159,23 @@ def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodi
                              f"{k + 1} apart (contact range {r2:.3f}); use fewer strips")
     strip_of_particle = strip_of_body[bodies]
     parts = []
-    link_strip = strip_of_particle[scene.links_ab[:, 0].astype(np.int64)] if scene.n_links else np.zeros(0, np.int64)
+    lab = scene.links_ab.astype(np.int64) if scene.n_links else np.zeros((0, 2), np.int64)
+    sa, sb = strip_of_particle[lab[:, 0]], strip_of_particle[lab[:, 1]]
+    is_cross = sa != sb
+    if is_cross.any() and not cut_bodies:
+        raise ValueError("a link crosses strips: bodies must be whole (or partition with cut_bodies=True)")
+    if (np.abs(sa - sb) > 1).any():
+        raise ValueError("a link spans more than two neighbouring strips: use fewer strips")
+    link_strip = np.where(is_cross, -1, sa)
+    xsel = np.nonzero(is_cross)[0]                      # cross links, scene order
+    xcol = cross_link_colours(lab[xsel]) if len(xsel) else np.zeros(0, np.int64)
+    n_xcol = int(xcol.max()) + 1 if len(xsel) else 0
     for k in range(world):
         sel = np.nonzero(strip_of_particle == k)[0]
         remap = np.full(n, -1, np.int64)
         remap[sel] = np.arange(len(sel))
         lsel = np.nonzero(link_strip == k)[0]
-        ab = remap[scene.links_ab[lsel].astype(np.int64)]
-        if (ab < 0).any():
-            raise ValueError("a link crosses strips: bodies must be whole")
+        ab = remap[lab[lsel]]
         local = replace(scene, name=f"{scene.name} [strip {k}/{world}]", particles=scene.particles[sel].copy(),
                         links_ab=ab.astype(np.uint32), links_len=scene.links_len[lsel].copy(), body_of=None)
         xl, xr = edges[k], edges[k + 1]
@@ -152,14 +185,56 @@ def partition_scene(scene: Scene, world: int, band: Optional[float] = None, bodi
             in_band = max(in_band, int((px < xl + band).sum()))
         if np.isfinite(xr):
             in_band = max(in_band, int((px > xr - band).sum()))
+        cross = None
+        if len(xsel):
+            # my share of the cross links, colour-major (scene order inside a colour)
+            mine_a, mine_b = sa[xsel] == k, sb[xsel] == k
+            my = np.nonzero(mine_a | mine_b)[0]
+            my = my[np.argsort(xcol[my], kind="stable")]
+            gl = xsel[my]
+            i_am_a = mine_a[my]
+            me = np.where(i_am_a, lab[gl, 0], lab[gl, 1])       # global index of my endpoint
+            other = np.where(i_am_a, lab[gl, 1], lab[gl, 0])
+            other_strip = strip_of_particle[other]
+            # what I receive from a neighbour = the sorted set of ITS endpoints of our common links; what I send to
+            # it = the sorted set of MINE (the neighbour computes the same two sets with the roles swapped)
+            recv = {side: np.unique(other[other_strip == k + d]) for side, d in ((0, -1), (1, +1))}
+            send = {side: np.unique(me[other_strip == k + d]) for side, d in ((0, -1), (1, +1))}
+            slot = np.where(other_strip == k - 1, np.searchsorted(recv[0], other),
+                            len(recv[0]) + np.searchsorted(recv[1], other))
+            cs = np.searchsorted(xcol[my], np.arange(n_xcol + 1))
+            cross = dict(mine=remap[me].astype(np.uint32), slot=slot.astype(np.uint32), i_am_a=i_am_a.astype(np.uint8),
+                         len=scene.links_len[gl].astype(f32), colour_start=cs.astype(np.uint32), n_colours=n_xcol,
+                         send_left=remap[send[0]].astype(np.uint32), send_right=remap[send[1]].astype(np.uint32),
+                         n_recv_left=len(recv[0]), n_recv_right=len(recv[1]), global_links=gl)
         parts.append(StripPart(k, world, local, sel, float(xl), float(xr), float(band), 0 if world == 1 else in_band,
                                float(margin_into[k - 1]) if k > 0 else None,
-                               float(margin_into[k + 1]) if k + 1 < world else None))
+                               float(margin_into[k + 1]) if k + 1 < world else None, cross, lsel))
     # both ends of an exchange use the same message size: one capacity for the whole chain
     cap = int(max(p.ghost_cap for p in parts) * cap_factor) + 1024 if world > 1 else 0
     for p in parts:
         p.ghost_cap = cap
     return parts
+
+
+def sequential_link_order(parts: List[StripPart], local_orders: List[np.ndarray]) -> np.ndarray:
+    """The sequential walk over the SCENE's links that the sharded run equals arithmetically:
+    [strip 0's links in its solver's schedule order][strip 1's] ... [cross links, colour-major, scene order inside
+    a colour].  `local_orders[k]` = strip k's Solver.link_order() (indices into its local link list).  Feed it to the
+    oracle (set_link_order) to replay a sharded run on one CPU thread."""
+    out = []
+    for p, lo in zip(parts, local_orders):
+        if p.local_links is not None and len(p.local_links):
+            out.append(np.asarray(p.local_links, np.int64)[np.asarray(lo, np.int64)])
+    seen = {}
+    for p in parts:
+        if p.cross is not None:
+            cs = p.cross["colour_start"]
+            for c in range(p.cross["n_colours"]):
+                seen.setdefault(c, set()).update(int(g) for g in p.cross["global_links"][cs[c]:cs[c + 1]])
+    for c in sorted(seen):
+        out.append(np.array(sorted(seen[c]), np.int64))
+    return np.concatenate(out).astype(np.uint32) if out else np.zeros(0, np.uint32)
 
 
 def replicated_state(sv: Solver):
@@ -178,9 +253,11 @@ def replicated_state(sv: Solver):
     return circles, polys
 
 
-def _load_part(part: StripPart, device: int, replicated=None) -> Solver:
+def _load_part(part: StripPart, device: int, replicated=None, link_schedule: str = "coloured") -> Solver:
     """`replicated` (from replicated_state) replaces the scene's initial Circles / polygons by their current state"""
     sv = Solver(device)
+    if link_schedule != "coloured":
+        sv.set_link_schedule(link_schedule)
     if replicated is None:
         part.scene.load_into(sv)
     else:
@@ -192,6 +269,15 @@ def _load_part(part: StripPart, device: int, replicated=None) -> Solver:
         for pos, prev, cen, st, ab, ln in polys:
             sv.add_polygon_raw(pos, ab, ln, st, cen, prev_xy=prev)
         sv.set_polygon_contact(part.scene.polygon_contact)
+    if part.cross is not None:
+        x = part.cross
+        up = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.POINTER(C.c_uint32))
+        sv._ck(sv._L.bendy_strip_set_cross_links(
+            sv._h, len(x["mine"]), up(x["mine"]), up(x["slot"]),
+            np.ascontiguousarray(x["i_am_a"]).ctypes.data_as(C.POINTER(C.c_uint8)),
+            np.ascontiguousarray(x["len"]).ctypes.data_as(C.POINTER(C.c_float)), x["n_colours"], up(x["colour_start"]),
+            len(x["send_left"]), up(x["send_left"]), len(x["send_right"]), up(x["send_right"]), x["n_recv_left"],
+            x["n_recv_right"]))
     if part.world > 1:
         sv._ck(sv._L.bendy_halo_configure(sv._h, part.ghost_cap, part.send_left_below, part.send_right_above,
                                           part.stray_left, part.stray_right))
@@ -280,9 +366,10 @@ class StripSolver(_StripBase):
     """One strip per process / GPU; halo over NCCL issued by the C library on its own stream."""
 
     def __init__(self, scene: Scene, rank: int, world: int, device: int, dist=None, band: Optional[float] = None,
-                 bodies: Optional[np.ndarray] = None):
+                 bodies: Optional[np.ndarray] = None, cut_bodies: bool = False, link_schedule: str = "coloured"):
         self.rank, self.world, self.dist, self.device_index = rank, world, dist, device
         self.full_scene, self.band = scene, band
+        self.cut_bodies, self.link_schedule = cut_bodies, link_schedule
         self.bodies = bodies if bodies is not None else scene.body_of
         self._uid = None
         self._build(scene, None)
@@ -291,8 +378,8 @@ class StripSolver(_StripBase):
         import torch
 
         rank, world, dist, device = self.rank, self.world, self.dist, self.device_index
-        self.part = partition_scene(scene, world, self.band, self.bodies)[rank]
-        self.solver = _load_part(self.part, device, replicated)
+        self.part = partition_scene(scene, world, self.band, self.bodies, cut_bodies=self.cut_bodies)[rank]
+        self.solver = _load_part(self.part, device, replicated, self.link_schedule)
         if prev is not None:
             self.solver.write_particles(prev_xy=prev[self.part.global_index])
         if world > 1:

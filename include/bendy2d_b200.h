@@ -206,6 +206,19 @@ int bendy_halo_configure(bendy_solver *s, uint32_t ghost_cap, float x_left, floa
                          float stray_right);
 /* restricts the broadphase grid to x in [x0, x1] (clipped to the bounds): a strip needs cells only
  * for its own discs and ghosts.  Results do not depend on it (the grid only prunes pairs). */
+/* Links whose two ends are owned by neighbouring strips (a body cut by a strip edge; the reference relaxes any link
+ * between any two particles: link.rs:18-27, loop solver.rs:144-146).  Each rank registers its share: link k joins
+ * MY particle mine[k] (user index) and the neighbour's particle that arrives in slot[k] of my link-ghost buffer
+ * (slots [0, n_recv_left) come from the left neighbour, the rest from the right one); i_am_a[k] tells which end I
+ * am (link.rs:22 computes a - b).  The links are sorted by colour (colour_start[n_colours + 1]; a colour holds
+ * vertex-disjoint links, and both ranks of a link use the same colour).  send_left / send_right: my particles whose
+ * positions the neighbour needs, in the order of ITS slots.  The cross colours run after all the strip's own
+ * links, every colour behind an exchange of the endpoint positions (NCCL transport only), which equals the
+ * sequential order [strip 0's schedule][strip 1's] ... [cross colour 0][cross colour 1] ... */
+int bendy_strip_set_cross_links(bendy_solver *s, size_t n, const uint32_t *mine, const uint32_t *slot, const uint8_t *i_am_a,
+                                const float *len, uint32_t n_colours, const uint32_t *colour_start, size_t n_send_left,
+                                const uint32_t *send_left, size_t n_send_right, const uint32_t *send_right,
+                                size_t n_recv_left, size_t n_recv_right);
 int bendy_set_grid_window(bendy_solver *s, float x0, float x1);
 /* rank 0 creates the NCCL id (128 bytes); the host layer (torch.distributed) broadcasts it */
 int bendy_nccl_unique_id(void *out128);

@@ -106,6 +106,10 @@ extern "C" {
     pub fn bendy_halo_configure(s: *mut bendy_solver, ghost_cap: u32, x_left: c_float, x_right: c_float,
                                 stray_left: c_float, stray_right: c_float) -> c_int;
     pub fn bendy_set_grid_window(s: *mut bendy_solver, x0: c_float, x1: c_float) -> c_int;
+    pub fn bendy_strip_set_cross_links(s: *mut bendy_solver, n: usize, mine: *const u32, slot: *const u32, i_am_a: *const u8,
+                                       len: *const c_float, n_colours: u32, colour_start: *const u32, n_send_left: usize,
+                                       send_left: *const u32, n_send_right: usize, send_right: *const u32,
+                                       n_recv_left: usize, n_recv_right: usize) -> c_int;
     pub fn bendy_nccl_unique_id(out128: *mut c_void) -> c_int;
     pub fn bendy_halo_comm_nccl(s: *mut bendy_solver, unique_id128: *const c_void, rank: c_int, world: c_int) -> c_int;
     pub fn bendy_halo_connect_local(left: *mut bendy_solver, right: *mut bendy_solver) -> c_int;

@@ -60,6 +60,7 @@ int main(void) {
     rc |= bendy_get_device_buffers(s, &p0, &p1, &np);
     rc |= bendy_halo_configure(s, 0, 0.f, 0.f, 0.f, 0.f);
     rc |= bendy_set_grid_window(s, 0.f, 1.f);
+    rc |= bendy_strip_set_cross_links(s, 0, NULL, NULL, NULL, NULL, 0, NULL, 0, NULL, 0, NULL, 0, 0);
     rc |= bendy_nccl_unique_id(uid);
     rc |= bendy_halo_comm_nccl(s, uid, 0, 1);
     rc |= bendy_halo_stats(s, &a, &b, &c, &d);

@@ -31,6 +31,10 @@ def _worker(rank, world, port, case, q):
 
     assert _lib.LIB_PATH.endswith("_emu.so")
     try:
+        if case in ("cut", "cut_ref"):
+            ok, info = _cut_bodies_case(rank, world, dist, case == "cut_ref")
+            q.put((rank, ok, info, 0, 1))
+            return
         if case in ("bodies", "polygons", "circles"):
             sc = touching_field() if world < 4 else touching_field(16, 2)
             if case == "polygons":
@@ -88,6 +92,67 @@ def _worker(rank, world, port, case, q):
         dist.destroy_process_group()
 
 
+def wide_bodies_scene():
+    """two lattice bodies 12.5 units wide (51 x 5 points, spacing 0.25) one above the other, touching discs: any cut
+    into 2 or 3 strips of equal particle count goes through both bodies"""
+    from bendy2d_b200 import scenes
+
+    pos0, ab0 = scenes.lattice_body(51, 5, 0.25, (0.0, 0.0), True)
+    pos = np.concatenate([pos0 + np.array([10.0, 6.0]), pos0 * np.array([1.0, 0.78]) + np.array([14.0, 7.3])]).astype(f32)
+    ab = np.concatenate([ab0, ab0 + len(pos0)]).astype(np.uint32)
+    d = pos[ab[:, 0]] - pos[ab[:, 1]]
+    ln = np.hypot(d[:, 0], d[:, 1]).astype(f32)
+    ln[len(ab0):] = (ln[len(ab0):] * f32(1.1)).astype(f32)  # the second body starts compressed: its links work from update 1
+    return scenes.Scene(name="wide bodies", bounds=(0.0, 0.0, 40.0, 12.0), particles=pos, links_ab=ab, links_len=ln,
+                        particle_radius=0.1)
+
+
+def _cut_bodies_case(rank, world, dist, reference_order, device=0):
+    """bodies cut by the strip edges: links across the edges run as trailing colours with an exchange of the endpoint
+    positions before each.  coloured schedule: the oracle replays the sharded run's sequential order; reference
+    order: with the scene's links listed in that order, sharded = unsharded = the oracle's insertion-order walk."""
+    from bendy2d_b200 import Solver, strips
+    from helpers import oracle_from_scene
+
+    sc = wide_bodies_scene()
+    n_updates = 40
+    if reference_order:
+        # list the links as [strip 0's][strip 1's] ... [cross, colour-major]: the order the sharded run executes
+        parts = strips.partition_scene(sc, world, cut_bodies=True)
+        order = strips.sequential_link_order(parts, [np.arange(len(p.local_links)) for p in parts])
+        sc.links_ab, sc.links_len = sc.links_ab[order].copy(), sc.links_len[order].copy()
+    sv = strips.StripSolver(sc, rank, world, device, dist, cut_bodies=True,
+                            link_schedule="reference" if reference_order else "coloured")
+    assert sv.part.cross is not None and len(sv.part.cross["mine"]) > 0, "the cut missed the bodies"
+    sv.update(sc.dt, n=n_updates)
+    sv.check_halo()
+    pos, prev = sv.read_particles()
+    gpos, gprev = strips.gather_global_state(dist, world, device, sv.part.global_index, pos, prev, sc.n_particles)
+    orders = [None] * world
+    dist.all_gather_object(orders, sv.link_order())
+    if rank != 0:
+        return True, "-"
+    parts = strips.partition_scene(sc, world, cut_bodies=True)
+    o = oracle_from_scene(sc)
+    o.set_grid(*sv.grid())
+    if not reference_order:
+        o.set_link_order(strips.sequential_link_order(parts, orders))
+    for _ in range(n_updates):
+        o.update(sc.dt)
+    op, oq = o.particles()
+    ok = np.array_equal(gpos.view(np.uint32), op.view(np.uint32)) and np.array_equal(gprev.view(np.uint32), oq.view(np.uint32))
+    info = f"cross links {sum(len(p.cross['mine']) for p in parts) // 2}, colours {parts[0].cross['n_colours']}"
+    if reference_order:
+        ref = Solver(device)
+        ref.set_link_schedule("reference")
+        sc.load_into(ref)
+        ref.update(sc.dt, n=n_updates)
+        rp, rq = ref.read_particles()
+        ok = ok and np.array_equal(gpos.view(np.uint32), rp.view(np.uint32)) and np.array_equal(gprev.view(np.uint32), rq.view(np.uint32))
+    moved = float(np.abs(gpos - sc.particles).max())
+    return bool(ok and moved > 0.5), info + f", max displacement {moved:.2f}"
+
+
 def _run(world, case, extra_env=None):
     import build as cuemu_build
     import torch.multiprocessing as mp
@@ -101,7 +166,7 @@ def _run(world, case, extra_env=None):
     try:
         ctx = mp.get_context("spawn")
         q = ctx.Queue()
-        port = 33500 + (os.getpid() % 2000) + 7 * world + {"bodies": 11, "polygons": 23, "circles": 37, "free_circles": 51}.get(case, 0)
+        port = 33500 + (os.getpid() % 2000) + 7 * world + {"bodies": 11, "polygons": 23, "circles": 37, "free_circles": 51, "cut": 63, "cut_ref": 77}.get(case, 0)
         procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
         for p in procs:
             p.start()
@@ -131,8 +196,7 @@ def _run(world, case, extra_env=None):
     return sorted(res)
 
 
-@pytest.mark.parametrize("world,extra", [(2, {}), (3, {"BENDY_HALO_FUSED": "1", "BENDY_SCAN_MT": "1", "BENDY_NARROW_DENSE": "1"}),
-                                         (4, {"BENDY_HALO_OVERLAP": "1"})])
+@pytest.mark.parametrize("world,extra", [(2, {}), (3, {"BENDY_PDL_NCCL": "0"}), (4, {"BENDY_HALO_OVERLAP": "1"})])
 def test_nccl_strip_solvers_match_the_single_solver_bit_for_bit(world, extra):
     res = _run(world, "bodies", extra)
     assert all(ok is True for _, ok, *_ in res), res
@@ -155,4 +219,11 @@ def test_nccl_strip_solvers_with_replicated_polygons():
 @pytest.mark.parametrize("world", [2, 3])
 def test_nccl_strip_solvers_with_replicated_circles_all_reduce_their_corrections(world):
     res = _run(world, "circles")
+    assert all(ok is True for _, ok, *_ in res), res
+
+
+@pytest.mark.parametrize("world,case", [(2, "cut"), (3, "cut"), (2, "cut_ref")])
+def test_bodies_cut_by_strip_edges_relax_their_cross_links_exactly(world, case):
+    """N6: links whose ends are owned by neighbouring ranks (link.rs:18-27 relaxes any link between any two particles)"""
+    res = _run(world, case)
     assert all(ok is True for _, ok, *_ in res), res

@@ -138,3 +138,48 @@ def test_nccl_strips_match_single_gpu():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert max_ulp(gp, rp) == 0 and max_ulp(gq, rq) == 0
+
+
+def _nccl_cut_worker(rank, world, port, reference_order, q):
+    import torch
+    import torch.distributed as dist
+
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        from test_emu_strips_mp import _cut_bodies_case
+
+        ok, info = _cut_bodies_case(rank, world, dist, reference_order, device=rank)
+        q.put((rank, ok, info))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:
+        q.put((rank, False, f"{type(e).__name__}: {e}"))
+        raise
+
+
+@pytest.mark.parametrize("reference_order", [False, True])
+def test_nccl_bodies_cut_by_strip_edges(reference_order):
+    """N6 on real NCCL: links across strip edges; sharded = oracle (replayed order) and, in reference order,
+    = the unsharded GPU run bit for bit"""
+    import torch
+
+    world = min(torch.cuda.device_count(), 3)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + (7 if reference_order else 0)
+    procs = [ctx.Process(target=_nccl_cut_worker, args=(r, world, port, reference_order, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for _ in procs:
+        rank, ok, info = q.get(timeout=300)
+        assert ok is True, f"rank {rank}: {info}"
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
