@@ -1503,7 +1503,18 @@ int bendy_save_snapshot(bendy_solver *s, const char *path) {
     return BENDY_OK;
 }
 
+static bendy_solver *load_snapshot_impl(const char *path, int device);
+
 bendy_solver *bendy_load_snapshot(const char *path, int device) {
+    try {  // nothing may unwind through the C boundary (a corrupt file must not take the host process down)
+        return load_snapshot_impl(path, device);
+    } catch (const std::exception &e) {
+        g_last_error = std::string("bendy_load_snapshot: ") + e.what();
+        return nullptr;
+    }
+}
+
+static bendy_solver *load_snapshot_impl(const char *path, int device) {
     if (!path) {
         g_last_error = "bendy_load_snapshot: null path";
         return nullptr;
@@ -1526,9 +1537,27 @@ bendy_solver *bendy_load_snapshot(const char *path, int device) {
         why = "unsupported snapshot version";
     else if (h.sub_steps == 0 || h.sub_steps > 0xFFFFu)
         why = "corrupt header (sub_steps)";
+    else if (!(h.particle_radius >= 0.f) || !(h.grid_cell >= 0.f) || !std::isfinite(h.particle_radius) || !std::isfinite(h.grid_cell))
+        why = "corrupt header (particle radius / grid cell: the setters only take finite values >= 0)";
     else {
         for (int i = 0; i < 7; i++)
             if (h.n[i] > 0x7FFFFFF0ull) why = "corrupt header (counts)";
+    }
+    if (!why) {
+        // the payload the counts announce must be exactly what is left of the file: checked BEFORE anything is
+        // allocated (a corrupt count must not ask for gigabytes)
+        const uint64_t nP = h.n[0], nC = h.n[1], nPoly = h.n[2], nG = h.n[3], nPL = h.n[4], nCL = h.n[5], nGL = h.n[6];
+        const uint64_t want = nP * 16 + (h.n[7] ? nP * 4 : 0) + nC * 28 + (h.n[8] ? nC * 4 : 0) + nPL * 12 + nCL * 12 +
+                              nPoly * sizeof(SnapPoly) + nG * 24 + nGL * 12;
+        const long here = ftell(f);
+        long end = -1;
+        if (here >= 0 && fseek(f, 0, SEEK_END) == 0) end = ftell(f);
+        if (here < 0 || end < 0 || fseek(f, here, SEEK_SET) != 0)
+            why = "cannot determine the file size";
+        else if ((uint64_t)(end - here) < want)
+            why = "truncated snapshot";
+        else if ((uint64_t)(end - here) > want)
+            why = "trailing bytes after the snapshot";
     }
     if (!why) {
         const uint64_t nP = h.n[0], nC = h.n[1], nPoly = h.n[2], nG = h.n[3], nPL = h.n[4], nCL = h.n[5], nGL = h.n[6];

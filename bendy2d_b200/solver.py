@@ -74,6 +74,12 @@ class Particle:  # particle.rs:5-18
     def add_force_v2(self, force):  # particle.rs:52-54
         self.acc = (self.acc + np.asarray(force, np.float32)).astype(np.float32)
 
+    def add_force_towards(self, point, force: float):  # particle.rs:56-59: acc += normalize(point - pos) * force
+        d = (np.asarray(point, np.float32) - self.pos).astype(np.float32)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            n = (d / _magnitude(d)).astype(np.float32)  # coincident points give NaN, like the reference
+            self.acc = (self.acc + n * np.float32(force)).astype(np.float32)
+
 
 @dataclass
 class Link:  # link.rs:5-10
@@ -137,8 +143,9 @@ class Polygon:  # polygon.rs:8-14
         angle = np.float32(0.0)
         step = np.float32(np.float32(2.0) * np.float32(math.pi)) / np.float32(point_count)
         for _ in range(point_count):
-            x = np.float32(radius) * np.float32(math.cos(float(angle)))
-            y = np.float32(radius) * np.float32(math.sin(float(angle)))
+            # f32::cos / f32::sin (polygon.rs:23-24): single-precision libm, not the double result rounded
+            x = np.float32(radius) * np.cos(angle, dtype=np.float32)
+            y = np.float32(radius) * np.sin(angle, dtype=np.float32)
             p = Particle((pos + np.array([x, y], np.float32)).astype(np.float32))
             pts.append(p)
             center = (center + p.pos).astype(np.float32)

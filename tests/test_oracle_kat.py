@@ -3,6 +3,8 @@
 The reference has no tests or golden vectors; these KATs are hand-derived from the cited source
 lines and evaluated independently here with numpy float32 in the same operator order.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -261,3 +263,17 @@ def test_ext_disc_contact_equals_reference_pair_rule_on_a_matching():
         hits += hit
         assert np.array_equal(bits(prev[2 * k]), bits(p1)) and np.array_equal(bits(prev[2 * k + 1]), bits(p2)), k
     assert hits > 300
+
+
+def test_ref_harness_pipeline():
+    """oracle/ref_harness (the cargo harness that pins the oracle against the real crate) end to end with the oracle
+    standing in for the crate: scene export, update counts (C1: 240 calls of dt/8 == 30 frames of 8 substeps),
+    output format and the bit compare against tests/golden/*.npz"""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "oracle", "ref_harness", "selfcheck.py")], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count(" OK") == 3

@@ -190,3 +190,26 @@ def test_snapshot_replays_into_the_oracle(tmp_path):
         o.update(sc.dt)
     st = compare_state(g, o, scale=512.0, what="snapshot replay")
     assert st["ulp_pos"] == 0 and st["ulp_prev"] == 0, st
+
+
+def test_corrupt_counts_are_refused_before_anything_is_allocated(tmp_path):
+    """a header that announces 2^31 particles in a 200-byte file must give 'truncated snapshot', not an
+    attempt to allocate 17 GB (std::bad_alloc through the C boundary)."""
+    import struct
+
+    s = snapshot_from_scene(scenes.c3_softbody_field(1, 1, 0, 0))
+    raw = bytearray(s.to_bytes())
+    off = 8 + 8 + 8 + 16 + 32  # magic, version/sub_steps, radius/cell, flags.., last[8] -> counts
+    raw[off:off + 8] = struct.pack("<Q", 0x7FFFFFF0)
+    p = tmp_path / "huge.b2d"
+    p.write_bytes(bytes(raw))
+    L = _lib.lib()
+    h = L.bendy_load_snapshot(str(p).encode(), -1)
+    assert not h
+    msg = (L.bendy_last_error(None) or b"").decode()
+    assert "truncated" in msg, msg
+    raw = bytearray(s.to_bytes())
+    raw[16:20] = struct.pack("<f", -1.0)  # particle_radius < 0: the setter would refuse it
+    p.write_bytes(bytes(raw))
+    assert not L.bendy_load_snapshot(str(p).encode(), -1)
+    assert "particle radius" in (L.bendy_last_error(None) or b"").decode()
