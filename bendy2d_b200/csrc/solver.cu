@@ -202,6 +202,7 @@ struct bendy_solver {
     float halo_xl = -INFINITY, halo_xr = INFINITY, stray_xl = -INFINITY, stray_xr = INFINITY;
     float win_x0 = -INFINITY, win_x1 = INFINITY;  // x-range the broadphase grid covers (clipped to the bounds)
     DevBuf<float2> d_send[2];
+    DevBuf<float> d_send_k[2];  // ext: inverse-mass scales of the packed discs
     DevBuf<uint32_t> d_send_cnt;
     ncclComm_t nccl_comm = nullptr;
     int comm_rank = -1, comm_world = 0;
@@ -476,12 +477,11 @@ int Ops::rebuild() {
     // Circle are summed over all strips (an integer all-reduce, hence order-free and bit-identical to the
     // unsharded sum) before the circles' tail applies them.  Inverse masses would need the neighbours' scales
     // next to the ghost positions: not yet.
-    if (s->halo_on && !s->p_k.empty())
-        return fail(BENDY_ERR_UNSUPPORTED,
-                    "strips (halo exchange) support free particles, particle links, circles and polygons: no inverse "
-                    "masses in a sharded solver yet");
-    if (s->halo_on && !s->c_k.empty())
-        return fail(BENDY_ERR_UNSUPPORTED, "strips (halo exchange): no inverse masses in a sharded solver yet");
+    // Inverse masses (ext): the scale of every packed disc travels with its position into the neighbour's ghost
+    // slots, so a ghost weighs in a contact exactly as it does on its owner.  Not combined with links across strip
+    // edges yet (the remote endpoint's scale would have to travel with the endpoint positions).
+    if (s->halo_on && (!s->p_k.empty() || !s->c_k.empty()) && !s->xl.empty())
+        return fail(BENDY_ERR_UNSUPPORTED, "strips: inverse masses together with links across strip edges are not supported yet");
     s->nG = (uint32_t)s->g_pos.size();
     s->N = s->nP + s->nC + s->nG;
     s->Npad = (s->N + 1u) & ~1u;
@@ -517,6 +517,8 @@ int Ops::rebuild() {
             CK(cudaFuncSetAttribute(k3_links_local<true, true, 0>, at, b));
             CK(cudaFuncSetAttribute(k3_links_local<false, true, 1>, at, b));
             CK(cudaFuncSetAttribute(k3_links_local<false, true, 2>, at, b));
+            CK(cudaFuncSetAttribute(k3_links_local<true, true, 1>, at, b));
+            CK(cudaFuncSetAttribute(k3_links_local<true, true, 2>, at, b));
         }
         // k_circles_exact: 45 KB of static tables + 12 B per circle (up to 4096 circles) of dynamic
         if (s->nC > 128 && s->nC <= 4096)
@@ -629,6 +631,8 @@ int Ops::rebuild() {
     }
     if (s->halo_on && s->ghost_cap) {
         for (int side = 0; side < 2; side++) CK(s->d_send[side].ensure(s->ghost_cap));
+        if (s->has_k)
+            for (int side = 0; side < 2; side++) CK(s->d_send_k[side].ensure(s->ghost_cap));
         CK(s->d_send_cnt.ensure(8));
         CK(cudaMemsetAsync(s->d_send_cnt.p, 0, 8 * sizeof(uint32_t), s->stream));
         k_halo_clear<<<cdiv(s->ghost_cap, 256), 256, 0, s->stream>>>(s->d_send[0].p, s->d_send[1].p, s->d_send_cnt.p,
@@ -807,14 +811,24 @@ int Ops::halo_exchange_nccl(cudaStream_t q) {
         return fail(BENDY_ERR_CUDA, std::string("NCCL error in ") + what + ": " + g_nccl.GetErrorString(r));
     };
     if (int rc = ck(g_nccl.GroupStart(), "ncclGroupStart")) return rc;
+    float *ghost_k = s->has_k ? s->d_k.p + s->nOwned : nullptr;  // the ghosts' inverse-mass scales travel along
     if (left >= 0) {
         if (int rc = ck(g_nccl.Send(s->d_send[0].p, nflt, ncclFloat, left, s->nccl_comm, q), "ncclSend")) return rc;
         if (int rc = ck(g_nccl.Recv(ghost, nflt, ncclFloat, left, s->nccl_comm, q), "ncclRecv")) return rc;
+        if (ghost_k) {
+            if (int rc = ck(g_nccl.Send(s->d_send_k[0].p, s->ghost_cap, ncclFloat, left, s->nccl_comm, q), "ncclSend")) return rc;
+            if (int rc = ck(g_nccl.Recv(ghost_k, s->ghost_cap, ncclFloat, left, s->nccl_comm, q), "ncclRecv")) return rc;
+        }
     }
     if (right < s->comm_world) {
         if (int rc = ck(g_nccl.Send(s->d_send[1].p, nflt, ncclFloat, right, s->nccl_comm, q), "ncclSend")) return rc;
         if (int rc = ck(g_nccl.Recv(ghost + s->ghost_cap, nflt, ncclFloat, right, s->nccl_comm, q), "ncclRecv"))
             return rc;
+        if (ghost_k) {
+            if (int rc = ck(g_nccl.Send(s->d_send_k[1].p, s->ghost_cap, ncclFloat, right, s->nccl_comm, q), "ncclSend")) return rc;
+            if (int rc = ck(g_nccl.Recv(ghost_k + s->ghost_cap, s->ghost_cap, ncclFloat, right, s->nccl_comm, q), "ncclRecv"))
+                return rc;
+        }
     }
     if (int rc = ck(g_nccl.GroupEnd(), "ncclGroupEnd")) return rc;
     if (s->capturing)
@@ -856,7 +870,9 @@ SubstepCtx Ops::make_ctx() {
                        c.halo ? s->d_send[0].p : nullptr,
                        c.halo ? s->d_send[1].p : nullptr,
                        c.halo ? s->d_send_cnt.p : nullptr,
-                       c.halo ? s->ghost_cap : 0u};
+                       c.halo ? s->ghost_cap : 0u,
+                       (c.halo && c.K) ? s->d_send_k[0].p : nullptr,
+                       (c.halo && c.K) ? s->d_send_k[1].p : nullptr};
     const LinkPlan &P = s->plan_p;
     c.n_in_parts = P.n_parts() ? P.part_start.back() : 0u;
     // the histogram (and the halo packing) must see the positions after ALL links: global colours and links that
@@ -884,7 +900,11 @@ int Ops::launch_links_local(const SubstepCtx &c, cudaStream_t q, uint32_t p0, ui
     const bool pdl = c.pdl > 0;
 #define K3L(HK, FC, HM) \
     LAUNCH(BENDY_K_LINKS_LOCAL, launch_k(pdl, k3_links_local<HK, FC, HM>, np, T, smem, q, pos, dk, 0u, ps, cs, ll, C, ca, p0))
-    if (c.fuse_count && halo_mode == 1)  // strips: no inverse masses (checked in rebuild)
+    if (c.K && c.fuse_count && halo_mode == 1)
+        K3L(true, true, 1);
+    else if (c.K && c.fuse_count && halo_mode == 2)
+        K3L(true, true, 2);
+    else if (c.fuse_count && halo_mode == 1)
         K3L(false, true, 1);
     else if (c.fuse_count && halo_mode == 2)
         K3L(false, true, 2);
@@ -973,9 +993,9 @@ int Ops::launch_count_unlinked(const SubstepCtx &c) {
     const uint32_t c0 = c.fuse_count ? c.n_in_parts : 0u;
     if (c0 >= s->nOwned) return BENDY_OK;
     if (c.halo)
-        LAUNCH(BENDY_K_GRID_BUILD, k2_count<true><<<cdiv(s->nOwned - c0, 256), 256, 0, c.st>>>(c.pos, c0, s->nOwned, c.ca));
+        LAUNCH(BENDY_K_GRID_BUILD, k2_count<true><<<cdiv(s->nOwned - c0, 256), 256, 0, c.st>>>(c.pos, c.dk, c0, s->nOwned, c.ca));
     else
-        LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_count<false>, cdiv(s->nOwned - c0, 256), 256, 0, c.st, c.pos, c0,
+        LAUNCH(BENDY_K_GRID_BUILD, launch_k(c.pdl > 0, k2_count<false>, cdiv(s->nOwned - c0, 256), 256, 0, c.st, c.pos, c.dk, c0,
                                             s->nOwned, c.ca));
     return BENDY_OK;
 }
@@ -989,7 +1009,7 @@ int Ops::launch_halo_receive(const SubstepCtx &c, cudaStream_t q_clear) {
         CK(cudaStreamWaitEvent(c.st, s->ev_xchg, 0));
     }
     LAUNCH(BENDY_K_GRID_BUILD,
-           k2_count<false><<<cdiv(s->nP - s->nOwned, 256), 256, 0, c.st>>>(c.pos, s->nOwned, s->nP, c.ca));
+           k2_count<false><<<cdiv(s->nP - s->nOwned, 256), 256, 0, c.st>>>(c.pos, c.dk, s->nOwned, s->nP, c.ca));
     return BENDY_OK;
 }
 
@@ -2290,6 +2310,10 @@ int bendy_update_group(bendy_solver **group, int n, uint32_t n_updates, float dt
                 // my left ghosts = the left peer's right-going send buffer, and vice versa
                 CK(cudaMemcpyAsync(s->d_pos.p + s->nOwned + (size_t)side * s->ghost_cap, p->d_send[1 - side].p, bytes,
                                    cudaMemcpyDeviceToDevice, s->stream));
+                if (s->has_k != p->has_k) return ops.fail(BENDY_ERR_ARG, "group members must all have (or all lack) inverse masses");
+                if (s->has_k)  // the ghosts' inverse-mass scales travel along
+                    CK(cudaMemcpyAsync(s->d_k.p + s->nOwned + (size_t)side * s->ghost_cap, p->d_send_k[1 - side].p,
+                                       (size_t)s->ghost_cap * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
             }
             CK(cudaEventRecord(s->ev_xchg, s->stream));
         }

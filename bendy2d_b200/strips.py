@@ -395,6 +395,15 @@ class StripSolver(_StripBase):
             raw = bytes(uid.cpu().tolist())
             self.solver._ck(L.bendy_halo_comm_nccl(self.solver._h, raw, rank, world))
 
+    def set_particle_inv_mass(self, k):
+        """ext: inverse-mass scale per particle of the FULL scene (user order); every rank keeps its own particles'.
+        A ghost carries its owner's scale: the scales of the packed discs travel with their positions."""
+        k = np.ascontiguousarray(k, f32).reshape(-1)
+        if len(k) != self.full_scene.n_particles:
+            raise ValueError("set_particle_inv_mass: one scale per particle of the full scene")
+        self._inv_mass = k
+        self.solver.set_particle_inv_mass(k[self.part.global_index])
+
     # ---- Solver surface
     def update(self, dt: float, n: int = 1):
         self.solver.update(dt, n)
@@ -455,6 +464,15 @@ class LocalStripGroup:
             if L.bendy_halo_connect_local(a._h, b._h) != 0:
                 raise RuntimeError((L.bendy_last_error(None) or b"").decode())
         self._handles = (C.c_void_p * len(self.solvers))(*[s._h for s in self.solvers])
+
+    def set_particle_inv_mass(self, k):
+        """ext: inverse-mass scale per particle of the full scene (user order)"""
+        k = np.ascontiguousarray(k, f32).reshape(-1)
+        if len(k) != self.scene.n_particles:
+            raise ValueError("set_particle_inv_mass: one scale per particle of the scene")
+        self._inv_mass = k
+        for p, s in zip(self.parts, self.solvers):
+            s.set_particle_inv_mass(k[p.global_index])
 
     def update(self, dt: float, n: int = 1):
         s0 = self.solvers[0]

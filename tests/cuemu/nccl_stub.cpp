@@ -57,11 +57,17 @@ void run_ops(void *arg) {
     while (true) {
         bool all = true, progress = false;
         std::vector<pollfd> pf;
+        std::vector<int> busy;  // FIFOs that already have an unfinished earlier op: NCCL matches the sends and
+                                // receives between two ranks in issue order, so a later op on the same FIFO waits
         for (size_t k = 0; k < ops.size(); k++) {
             Op &o = ops[k];
             if (done[k] == o.bytes) continue;
             all = false;
             const int fd = o.send ? o.comm->fd_out[o.peer] : o.comm->fd_in[o.peer];
+            bool wait = false;
+            for (int b : busy) wait = wait || b == fd;
+            if (wait) continue;
+            busy.push_back(fd);
             ssize_t r = o.send ? write(fd, o.buf + done[k], o.bytes - done[k]) : read(fd, o.buf + done[k], o.bytes - done[k]);
             if (r > 0) done[k] += (size_t)r, progress = true;
             pf.push_back(pollfd{fd, (short)(o.send ? POLLOUT : POLLIN), 0});

@@ -35,8 +35,13 @@ def _worker(rank, world, port, case, q):
             ok, info = _cut_bodies_case(rank, world, dist, case == "cut_ref")
             q.put((rank, ok, info, 0, 1))
             return
-        if case in ("bodies", "polygons", "circles"):
+        kmass = None
+        if case in ("bodies", "polygons", "circles", "kmass"):
             sc = touching_field() if world < 4 else touching_field(16, 2)
+            if case == "kmass":  # ext inverse masses: the packed discs' scales travel with their positions
+                rng = np.random.default_rng(5)
+                kmass = rng.choice([0.25, 0.5, 1.0, 2.0, 4.0], sc.n_particles).astype(f32)
+                kmass[rng.choice(sc.n_particles, 40, replace=False)] = 0.0
             if case == "polygons":
                 sc = touching_field(8, 2)  # two rows of bodies (y 8..23) above the obstacles  # replicated obstacles under the bodies, one dynamic overlapping pair
                 src = scenes.c3_softbody_field(2, 1, 0, 10)
@@ -52,6 +57,8 @@ def _worker(rank, world, port, case, q):
                 sc.circles_pos[3] = sc.circles_pos[2] + np.array([0.8, 0.3], f32)
                 sc.circles_r = np.array([1.2, 0.9, 1.1, 1.0, 1.4, 0.8, 1.3, 1.0, 0.7, 1.2], f32)
             sv = strips.StripSolver(sc, rank, world, 0, dist)
+            if kmass is not None:
+                sv.set_particle_inv_mass(kmass)
             rounds = 3 if case == "bodies" else 2  # later the bodies bounce off the obstacles past the stray margin
             for _ in range(rounds):
                 sv.update(sc.dt, n=20)
@@ -76,6 +83,8 @@ def _worker(rank, world, port, case, q):
         if rank == 0 or case in ("circles", "free_circles"):
             ref = Solver()
             sc.load_into(ref)
+            if kmass is not None:
+                ref.set_particle_inv_mass(kmass)
             ref.update(sc.dt, n=n_updates)
             rp, rq = ref.read_particles()
             ok = np.array_equal(gpos.view(np.uint32), rp.view(np.uint32)) and np.array_equal(gprev.view(np.uint32), rq.view(np.uint32))
@@ -166,7 +175,7 @@ def _run(world, case, extra_env=None):
     try:
         ctx = mp.get_context("spawn")
         q = ctx.Queue()
-        port = 33500 + (os.getpid() % 2000) + 7 * world + {"bodies": 11, "polygons": 23, "circles": 37, "free_circles": 51, "cut": 63, "cut_ref": 77}.get(case, 0)
+        port = 33500 + (os.getpid() % 2000) + 7 * world + {"bodies": 11, "polygons": 23, "circles": 37, "free_circles": 51, "cut": 63, "cut_ref": 77, "kmass": 91}.get(case, 0)
         procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
         for p in procs:
             p.start()
@@ -227,3 +236,9 @@ def test_bodies_cut_by_strip_edges_relax_their_cross_links_exactly(world, case):
     """N6: links whose ends are owned by neighbouring ranks (link.rs:18-27 relaxes any link between any two particles)"""
     res = _run(world, case)
     assert all(ok is True for _, ok, *_ in res), res
+
+
+def test_nccl_strip_solvers_with_inverse_masses():
+    res = _run(2, "kmass")
+    assert all(ok is True for _, ok, *_ in res), res
+    assert sum(r[2] for r in res) > 0

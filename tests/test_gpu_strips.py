@@ -82,15 +82,22 @@ def test_strip_group_sub_steps():
     assert max_ulp(grp.read_particles()[0], ref.read_particles()[0]) == 0
 
 
-def _nccl_worker(rank, world, port, q):
+def _inv_masses(n):
+    rng = np.random.default_rng(5)
+    k = rng.choice([0.25, 0.5, 1.0, 2.0, 4.0], n).astype(f32)
+    k[rng.choice(n, 40, replace=False)] = 0.0  # pinned points
+    return k
+
+
+def _nccl_worker(rank, world, port, q, with_k=False):
     try:
-        _nccl_worker_body(rank, world, port, q)
+        _nccl_worker_body(rank, world, port, q, with_k)
     except Exception as e:  # report instead of leaving the parent waiting for the queue
         q.put((rank, None, None, None, f"{type(e).__name__}: {e}"))
         raise
 
 
-def _nccl_worker_body(rank, world, port, q):
+def _nccl_worker_body(rank, world, port, q, with_k):
     import torch
     import torch.distributed as dist
 
@@ -100,6 +107,8 @@ def _nccl_worker_body(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     sc = touching_field(24, 2)  # wide enough that every strip has interior bodies (overlapped exchange path)
     sv = strips.StripSolver(sc, rank, world, rank, dist)
+    if with_k:
+        sv.set_particle_inv_mass(_inv_masses(sc.n_particles))
     info = sv.schedule_info()
     sv.update(sc.dt, n=60)
     pos, prev = sv.read_particles()
@@ -109,7 +118,9 @@ def _nccl_worker_body(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_nccl_strips_match_single_gpu():
+@pytest.mark.parametrize("with_k", [False, True])
+def test_nccl_strips_match_single_gpu(with_k):
+    """with_k: ext inverse masses - the packed discs' scales travel with their positions (two more messages)"""
     import torch
 
     world = min(torch.cuda.device_count(), 4)
@@ -120,12 +131,14 @@ def test_nccl_strips_match_single_gpu():
     sc = touching_field(24, 2)
     ref = Solver(0)
     sc.load_into(ref)
+    if with_k:
+        ref.set_particle_inv_mass(_inv_masses(sc.n_particles))
     ref.update(sc.dt, n=60)
     rp, rq = ref.read_particles()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + (3 if with_k else 0)
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q, with_k)) for r in range(world)]
     for p in procs:
         p.start()
     gp, gq = np.empty_like(rp), np.empty_like(rq)

@@ -1,10 +1,11 @@
-"""Strips with replicated polygons and circles (written after the round's GPU budget was spent: so far they have
-only run on the CPU emulation, hence in a file that sorts behind the device-proven tests)."""
+"""Strips with replicated polygons and circles, and with inverse masses (bit-identical to the unsharded run; the
+replicated-circles all-reduce and the NCCL path ran on 2 x B200 in round 2: profiles/r2_strips_2gpu_*.txt)."""
 import numpy as np
 import pytest
 
 from bendy2d_b200 import Solver, scenes, strips
 from helpers import bits, max_ulp
+from test_gpu_strips import touching_field
 
 pytestmark = pytest.mark.gpu
 f32 = np.float32
@@ -85,3 +86,31 @@ def test_strips_with_replicated_circles_match_single_solver():
     still.bounds.size[:] = (128.0, 64.0)
     still.update(sc.dt, n=20 * checked)
     assert not np.array_equal(bits(still.read_circles()[0]), bits(rc[0]))
+
+
+def test_strips_with_inverse_masses_match_single_solver():
+    """ext inverse masses in a sharded run: a ghost disc weighs in a contact exactly as on its owner (its scale
+    travels with its position), pinned discs (k = 0) stay put on either side of an edge"""
+    sc = touching_field(8, 2)
+    rng = np.random.default_rng(5)
+    k = rng.choice([0.25, 0.5, 1.0, 2.0, 4.0], sc.n_particles).astype(f32)
+    k[rng.choice(sc.n_particles, 40, replace=False)] = 0.0  # pinned points
+    ref = Solver()
+    sc.load_into(ref)
+    ref.set_particle_inv_mass(k)
+    grp = strips.LocalStripGroup(sc, 3)
+    grp.set_particle_inv_mass(k)
+    for step in range(4):
+        ref.update(sc.dt, n=15)
+        grp.update(sc.dt, n=15)
+        rp, rq = ref.read_particles()
+        gp, gq = grp.read_particles()
+        assert max_ulp(gp, rp) == 0 and max_ulp(gq, rq) == 0, f"after {15 * (step + 1)} substeps"
+    stats = grp.halo_stats()
+    assert all(o == 0 and st == 0 for _, _, o, st in stats), stats
+    assert sum(a + b for a, b, _, _ in stats) > 0
+    # and the weighted rule is really in play: the same run with unit masses ends elsewhere
+    unit = Solver()
+    sc.load_into(unit)
+    unit.update(sc.dt, n=60)
+    assert not np.array_equal(unit.read_particles()[0], rp)
