@@ -62,10 +62,10 @@ def test_emulator_primitives_self_check(emu_lib, tmp_path):
         assert r.returncode != 0 and msg in r.stderr, (mode, r.stdout, r.stderr)
 
 
-def test_grid_barrier_kernels_time_out_instead_of_hanging(emu_lib, tmp_path):
-    """kernel-level (tests/cuemu/kernel_unit.cpp): k2_scan_scatter_fused / k2_scan_fused_mt on a resident grid sort /
-    scan correctly; on a grid larger than the device their software barrier gives up, raises the flag and every
-    CTA leaves"""
+def test_counting_sort_with_the_one_pass_scan_at_kernel_level(emu_lib, tmp_path):
+    """kernel-level (tests/cuemu/kernel_unit.cpp): k2_count (histogram + scan-tile totals, CTA tables overflowing),
+    k2_scan and k2_scatter checked cell by cell, on a grid smaller and one larger than the emulated device (the
+    scan has no inter-CTA barrier any more, so nothing depends on residency)"""
     build_dir = os.path.join(HERE, "cuemu", "_build")
     exe = tmp_path / "kernel_unit"
     subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-w", "-ffp-contract=off",
