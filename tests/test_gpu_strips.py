@@ -196,3 +196,70 @@ def test_nccl_bodies_cut_by_strip_edges(reference_order):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+
+
+def _nccl_rebalance_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        # free particles pile up and spread sideways: ownership has to follow (rebalance over the process group);
+        # replicated Circles in the pile: their state must survive the re-partition
+        sc = scenes.c2_free_particles(80, 30)
+        sc.bounds = (0.0, 0.0, 48.0, 12.0)
+        sc.circles_pos = np.array([[18.0, 10.5], [24.0, 10.8], [30.0, 10.2]], f32)
+        sc.circles_r = np.array([0.9, 0.6, 1.1], f32)
+        sv = strips.StripSolver(sc, rank, world, rank, dist, band=4.0)
+        n_updates, rebalanced = 150, 0
+        for _ in range(n_updates):
+            sv.update(sc.dt)
+            if sv.needs_rebalance():
+                sv.rebalance()
+                rebalanced += 1
+        pos, prev = sv.read_particles()
+        gpos, gprev = strips.gather_global_state(dist, world, rank, sv.part.global_index, pos, prev, sc.n_particles)
+        ok = True
+        if rank == 0:
+            ref = Solver(rank)
+            sc.load_into(ref)
+            ref.update(sc.dt, n=n_updates)
+            rp, rq = ref.read_particles()
+            ok = max_ulp(gpos, rp) == 0 and max_ulp(gprev, rq) == 0
+            a, b = sv.read_circles(), ref.read_circles()
+            ok = ok and max_ulp(a[0], b[0]) == 0 and max_ulp(a[1], b[1]) == 0
+        q.put((rank, ok, rebalanced))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:
+        q.put((rank, False, f"{type(e).__name__}: {e}"))
+        raise
+
+
+def test_nccl_rebalance_over_the_process_group():
+    """StripSolver.rebalance() on real NCCL (only the CPU emulation had run it): re-partition by the
+    current positions, bit-identical continuation, replicated Circles carried across"""
+    import torch
+
+    world = min(torch.cuda.device_count(), 3)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 32500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_nccl_rebalance_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = []
+    for _ in procs:
+        res.append(q.get(timeout=600))
+        assert res[-1][1] is True, f"rank {res[-1][0]}: {res[-1][2]}"
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert max(r[2] for r in res) > 0, "the scene never needed rebalancing: nothing was tested"
