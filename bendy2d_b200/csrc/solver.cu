@@ -2425,3 +2425,17 @@ int bendy_plan_links_scheduled(size_t n_points, const uint32_t *ab, size_t n_lin
 }
 
 }  // extern "C"
+
+#ifdef BENDY_TIMESTAMPS
+// measurement builds only (profiles/substep_timeline.py): reset / read the per-SM kernel time stamps
+extern "C" int bendy_debug_ts_reset() {
+    static unsigned long long h[4][3][256];
+    for (auto &k : h)
+        for (int w = 0; w < 3; w++)
+            for (int i = 0; i < 256; i++) k[w][i] = w == 2 ? 0ull : ~0ull;
+    return cudaMemcpyToSymbol(bendy::g_ts, h, sizeof h) == cudaSuccess ? 0 : -3;
+}
+extern "C" int bendy_debug_ts_read(unsigned long long *out) {
+    return cudaMemcpyFromSymbol(out, bendy::g_ts, sizeof(unsigned long long) * 4 * 3 * 256) == cudaSuccess ? 0 : -3;
+}
+#endif
