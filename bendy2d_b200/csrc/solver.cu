@@ -123,8 +123,8 @@ struct PendingEvent {
 struct bendy_solver {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[2] = {nullptr, nullptr};  // graph branches: circles, polygons
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_main = nullptr;
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // graph branches: circles, polygons, work statistics
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_main = nullptr;
     std::string err;
     int sticky = BENDY_OK;
 
@@ -178,6 +178,14 @@ struct bendy_solver {
                                 // on the NCCL strip path (BENDY_PDL_NCCL=1)
     bool pdl_nccl = true;   // BENDY_PDL_NCCL=0 turns programmatic dependent launch off on the strip path
     DevBuf<float2> d_sorted_pos;
+    // which end of the index range the narrowphase starts at (kernels.cuh, k_work_halves)
+    DevBuf<uint32_t> d_chunk_work;                // clocks / 64 per warp of the narrowphase
+    unsigned long long *h_work_halves = nullptr;  // pinned: their sums over the lower / upper half of the chunks, written
+                                                  // by k_work_halves once per update, read (possibly a few updates
+                                                  // stale) when the next one is enqueued
+    int narrow_order_mode = 0;   // BENDY_NARROW_ORDER: 0 = auto (default), 1 = forward, 2 = reverse
+    bool narrow_reverse = true;  // current choice; auto starts at the top: bodies created last tend to be the lowest
+    bool record_work = false;    // set for the LAST substep of an update: only that one pays for the clocks
     DevBuf<uint32_t> d_circ_tile_count, d_circ_tile_ids;
     uint32_t n_scan_tiles = 0, n_circ_tiles = 0;
     DevBuf<unsigned long long> d_circ_acc;
@@ -301,6 +309,9 @@ struct Ops {  // helper with access to the solver; keeps bendy_solver a plain st
     int grid_for(float bx, float by, float bw, float bh, StepParams *p, uint32_t *ncells);
     int enqueue_substeps(uint32_t count);
     int launch_substep(int phase = PHASE_ALL);
+    int end_update(cudaStream_t q);
+    bool work_stats_on() const;
+    void choose_narrow_order();
     int halo_exchange_nccl(cudaStream_t q);
     SubstepCtx make_ctx();
     int launch_links_local(const SubstepCtx &c, cudaStream_t q, uint32_t p0, uint32_t p1, int halo_mode);
@@ -628,6 +639,11 @@ int Ops::rebuild() {
         CK(s->d_sorted_id.ensure(s->nP));
         CK(s->d_slot_of.ensure(s->nP));
         CK(s->d_sorted_pos.ensure(s->nP));
+        const size_t n_work = (size_t)cdiv(s->nOwned ? s->nOwned : 1u, NARROW_THREADS) * NARROW_WARPS;
+        CK(s->d_chunk_work.ensure(n_work));
+        CK(cudaMemsetAsync(s->d_chunk_work.p, 0, n_work * sizeof(uint32_t), s->stream));
+        if (!s->h_work_halves) CK(cudaHostAlloc(&s->h_work_halves, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+        s->h_work_halves[0] = s->h_work_halves[1] = 0ull;
     }
     if (s->halo_on && s->ghost_cap) {
         for (int side = 0; side < 2; side++) CK(s->d_send[side].ensure(s->ghost_cap));
@@ -1114,10 +1130,10 @@ int Ops::launch_collide_integrate_discs(const SubstepCtx &c, int phase) {
     if (phase == PHASE_C) return launch_circle_tail(c);  // same-process strips: the corrections were summed by the group
     K2Args a{c.pos,    s->d_prev.p, c.dk,  s->d_slot_of.p, s->d_sorted_id.p,       s->d_sorted_pos.p,    s->d_cell_start.p, s->n_cells,
              s->nP,    s->nOwned,   s->nC, s->d_crad.p,    s->d_circ_tile_count.p, s->d_circ_tile_ids.p, s->d_circ_acc.p,
-             s->d_circ_snap.p};
-    const uint32_t blocks = cdiv(s->nOwned, 128);
+             s->d_circ_snap.p, s->record_work ? s->d_chunk_work.p : nullptr, s->narrow_reverse ? 1u : 0u};
+    const uint32_t blocks = cdiv(s->nOwned, NARROW_THREADS);
 #define NARROW(HK, HP) \
-    LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_contact_integrate<HK, HP>, blocks, 128, 0, st, a, c.k4, c.prm))
+    LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_contact_integrate<HK, HP>, blocks, NARROW_THREADS, 0, st, a, c.k4, c.prm))
     if (c.K && c.contact)
         NARROW(true, true);
     else if (c.K)
@@ -1243,6 +1259,39 @@ int Ops::launch_substep(int phase) {
     return c.discs ? launch_collide_integrate_discs(c, phase) : launch_collide_integrate_plain(c);
 }
 
+// once per update(): the work the narrowphase's warps recorded, summed per half of the index range, goes to the
+// host.  In a captured graph this is a branch of its own that runs beside the update's first substeps (the figures
+// it carries are those of the update before, give or take the substep already running - they steer a heuristic,
+// nothing else).
+bool Ops::work_stats_on() const { return s->particle_radius > 0.f && s->nP && s->d_chunk_work.p && s->h_work_halves; }
+int Ops::end_update(cudaStream_t q) {
+    if (!work_stats_on()) return BENDY_OK;
+    // (pinned host memory is addressable from the device: the two sums are written straight into it)
+    LAUNCH(BENDY_K_GRID_BUILD, k_work_halves<<<1, 1024, 0, q>>>(s->d_chunk_work.p, cdiv(s->nOwned, NARROW_THREADS), s->h_work_halves));
+    return BENDY_OK;
+}
+
+// before an update is enqueued: start the narrowphase at the end of the index range that cost more (by a quarter)
+// in the most recent update whose figures have arrived; a captured graph has the choice baked in
+void Ops::choose_narrow_order() {
+    bool want = s->narrow_reverse;
+    if (s->narrow_order_mode == 1)
+        want = false;
+    else if (s->narrow_order_mode == 2)
+        want = true;
+    else if (s->h_work_halves) {
+        const unsigned long long lo = s->h_work_halves[0], hi = s->h_work_halves[1];
+        if (hi > lo + lo / 4)
+            want = true;
+        else if (lo > hi + hi / 4)
+            want = false;
+    }
+    if (want != s->narrow_reverse) {
+        s->narrow_reverse = want;
+        drop_graph();
+    }
+}
+
 int Ops::build_graph(uint32_t substeps) {
     drop_graph();
     cudaGraph_t graph = nullptr;
@@ -1256,7 +1305,19 @@ int Ops::build_graph(uint32_t substeps) {
     if (use_c || use_g) ce = cudaEventRecord(s->ev_fork, s->stream);
     if (ce == cudaSuccess && use_c) ce = cudaStreamWaitEvent(s->side[0], s->ev_fork, 0);
     if (ce == cudaSuccess && use_g) ce = cudaStreamWaitEvent(s->side[1], s->ev_fork, 0);
-    for (uint32_t k = 0; k < substeps && rc == BENDY_OK && ce == cudaSuccess; k++) rc = launch_substep();
+    const bool use_w = work_stats_on();
+    if (use_w && ce == cudaSuccess) {
+        if (!(use_c || use_g)) ce = cudaEventRecord(s->ev_fork, s->stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s->side[2], s->ev_fork, 0);
+        if (ce == cudaSuccess) rc = end_update(s->side[2]);
+    }
+    for (uint32_t k = 0; k < substeps && rc == BENDY_OK && ce == cudaSuccess; k++) {
+        s->record_work = k + 1 == substeps;
+        rc = launch_substep();
+    }
+    s->record_work = false;
+    if (ce == cudaSuccess && use_w) ce = cudaEventRecord(s->ev_join[2], s->side[2]);
+    if (ce == cudaSuccess && use_w) ce = cudaStreamWaitEvent(s->stream, s->ev_join[2], 0);
     if (ce == cudaSuccess && use_c) ce = cudaEventRecord(s->ev_join[0], s->side[0]);
     if (ce == cudaSuccess && use_c) ce = cudaStreamWaitEvent(s->stream, s->ev_join[0], 0);
     if (ce == cudaSuccess && use_g) ce = cudaEventRecord(s->ev_join[1], s->side[1]);
@@ -1284,14 +1345,20 @@ int Ops::build_graph(uint32_t substeps) {
 int Ops::enqueue_substeps(uint32_t updates) {
     const uint32_t S = s->sub_steps;
     uint32_t done = 0;
+    choose_narrow_order();
     // the first substep after circles/polygons were added with a pending acc runs eagerly with the
     // accel variant of K1 (particle.rs:23-24); afterwards acc == 0 and gravity is fused.
     if (s->accel_pending) {
         if (int rc = launch_substep()) return rc;
         s->accel_pending = false;
         drop_graph();
-        for (uint32_t k = 1; k < S; k++)
-            if (int rc = launch_substep()) return rc;
+        for (uint32_t k = 1; k < S; k++) {
+            s->record_work = k + 1 == S;
+            int rc = launch_substep();
+            s->record_work = false;
+            if (rc) return rc;
+        }
+        if (int rc = end_update(s->stream)) return rc;
         done = 1;
     }
     if (done == updates) return BENDY_OK;
@@ -1309,9 +1376,15 @@ int Ops::enqueue_substeps(uint32_t updates) {
         return BENDY_OK;
     }
     if (s->profiling) {
-        for (uint32_t u = done; u < updates; u++)
-            for (uint32_t k = 0; k < S; k++)
-                if (int rc = launch_substep()) return rc;
+        for (uint32_t u = done; u < updates; u++) {
+            for (uint32_t k = 0; k < S; k++) {
+                s->record_work = k + 1 == S;
+                int rc = launch_substep();
+                s->record_work = false;
+                if (rc) return rc;
+            }
+            if (int rc = end_update(s->stream)) return rc;
+        }
         return BENDY_OK;
     }
     if (!s->graph_exec || s->graph_substeps != S)
@@ -1336,6 +1409,7 @@ bendy_solver::~bendy_solver() {
     for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
     if (t0) cudaEventDestroy(t0);
     if (t1) cudaEventDestroy(t1);
+    if (h_work_halves) cudaFreeHost(h_work_halves);
     if (h_prm_ring) {
         for (uint32_t i = 0; i < kPrmRing; i++)
             if (prm_ring_ev[i]) cudaEventDestroy(prm_ring_ev[i]);
@@ -1344,7 +1418,7 @@ bendy_solver::~bendy_solver() {
     if (nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(nccl_comm);
     for (int sd = 0; sd < 2; sd++)
         if (peer[sd]) peer[sd]->peer[1 - sd] = nullptr;
-    for (cudaEvent_t e : {ev_fork, ev_join[0], ev_join[1], ev_main, ev_phase_a, ev_xchg})
+    for (cudaEvent_t e : {ev_fork, ev_join[0], ev_join[1], ev_join[2], ev_main, ev_phase_a, ev_xchg})
         if (e) cudaEventDestroy(e);
     for (cudaStream_t q : side)
         if (q) cudaStreamDestroy(q);
@@ -1396,6 +1470,10 @@ bendy_solver *bendy_create(int device) {
         if (t >= 32 && t <= 1024 && t % 32 == 0) s->k3_threads = (uint32_t)t;
     }
     if (const char *v = getenv("BENDY_HALO_OVERLAP")) s->halo_overlap = atoi(v) != 0;
+    if (const char *v = getenv("BENDY_NARROW_ORDER")) {
+        s->narrow_order_mode = !strcmp(v, "forward") ? 1 : (!strcmp(v, "reverse") ? 2 : 0);
+        if (s->narrow_order_mode) s->narrow_reverse = s->narrow_order_mode == 2;
+    }
     if (const char *v = getenv("BENDY_SMALL_SCENE")) s->small_scene = atoi(v) != 0;
     if (const char *v = getenv("BENDY_POLY_FUSED")) s->poly_fused = atoi(v) != 0;
     if (const char *v = getenv("BENDY_PDL")) s->pdl = atoi(v);
@@ -1413,6 +1491,8 @@ bendy_solver *bendy_create(int device) {
         (e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&s->side[0], cudaStreamNonBlocking, prio_side)) != cudaSuccess ||
         (e = cudaStreamCreateWithPriority(&s->side[1], cudaStreamNonBlocking, prio_side)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&s->side[2], cudaStreamNonBlocking, prio_side)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&s->ev_join[2], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&s->ev_join[0], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&s->ev_join[1], cudaEventDisableTiming)) != cudaSuccess ||
@@ -2106,7 +2186,7 @@ int bendy_get_stats(bendy_solver *s, uint64_t *out, int n) {
     for (int k = 0; k < n; k++) out[k] = 0;
     if (n > 4) out[4] = s->n_scan_tiles;
     if (n > 5) out[5] = s->n_cells;
-    if (n > 6) out[6] = 0;
+    if (n > 6) out[6] = s->narrow_reverse ? 1 : 0;  // the narrowphase currently starts at the top of the index range
     if (!s->d_flags.p) return BENDY_OK;
     if (int rc = ops.bind()) return rc;
     int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};

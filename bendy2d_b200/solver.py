@@ -456,7 +456,7 @@ class Solver:
         out = (C.c_uint64 * 8)()
         self._ck(self._L.bendy_get_stats(self._h, out, 8))
         return {"circle_pass_fallbacks": int(out[0]), "by_path_bound": int(out[1]), "by_list_overflow": int(out[2]),
-                "by_scale": int(out[3]), "scan_tiles": int(out[4]), "grid_cells": int(out[5])}
+                "by_scale": int(out[3]), "scan_tiles": int(out[4]), "grid_cells": int(out[5]), "narrow_reverse": int(out[6])}
 
     def launch_count(self) -> int:
         return int(self._L.bendy_launch_count(self._h))

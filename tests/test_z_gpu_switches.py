@@ -99,8 +99,34 @@ def test_discs_spread_over_hundreds_of_scan_tiles_per_cta():
     assert (np.abs(p[:n, 0] - p[n:, 0]) > 0.16).all(), "the pairs were pushed apart: the contacts were found"
 
 
+def test_narrowphase_starts_at_the_heavier_end_of_the_index_range():
+    """auto mode: the host reads the clocks the narrowphase's warps recorded per half of the index range and starts
+    the next update at the heavier end; a crowd among the FIRST discs turns the default (top down) around, a crowd
+    among the LAST ones turns it back.  (Which end comes first never changes a result: next test.)"""
+    rng = np.random.default_rng(11)
+    n = 4096
+
+    def scene(crowd_first):
+        spread = np.stack([2.0 + 60.0 * rng.random(n), 2.0 + 28.0 * rng.random(n)], 1)       # nobody touches anybody
+        crowd = np.stack([30.0 + 1.5 * rng.random(n), 10.0 + 1.5 * rng.random(n)], 1)        # everybody touches dozens
+        pos = np.concatenate([crowd, spread] if crowd_first else [spread, crowd]).astype(f32)
+        return scenes.Scene(name="crowd", particles=pos, bounds=(0.0, 0.0, 64.0, 32.0), particle_radius=0.1, sub_steps=2)
+
+    for crowd_first, want in ((True, 0), (False, 1)):
+        with env(BENDY_NARROW_ORDER="auto"):
+            g = Solver()
+        sc = scene(crowd_first)
+        sc.load_into(g)
+        assert g.stats()["narrow_reverse"] == 1  # the default
+        for _ in range(4):  # the figures of update k travel beside update k + 1 and are read when k + 2 is enqueued
+            g.update(sc.dt)
+            g.synchronize()
+        assert g.stats()["narrow_reverse"] == want, (crowd_first, g.stats())
+
+
 @pytest.mark.parametrize("switches", [{"BENDY_PDL": 0}, {"BENDY_PDL": 1}, {"BENDY_PDL": 2}, {"BENDY_K3_THREADS": 256},
-                                      {"BENDY_K3_THREADS": 64}])
+                                      {"BENDY_K3_THREADS": 64}, {"BENDY_NARROW_ORDER": "forward"},
+                                      {"BENDY_NARROW_ORDER": "reverse"}])
 def test_scheduling_switches_do_not_change_results(switches):
     sc = scenes.c3_softbody_field(4, 3, 3, 4)
     ref = run(sc, 40)
