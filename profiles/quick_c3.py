@@ -16,6 +16,8 @@ sv = Solver()
 sc.load_into(sv)
 if len(sys.argv) > 2:
     sv.set_plan_params(int(sys.argv[2]), 0)
+if os.environ.get("QUICK_C3_CELL"):  # broadphase cell size (default: auto = 4.2 r_p)
+    sv.set_grid_cell(float(os.environ["QUICK_C3_CELL"]))
 sv.update(sc.dt, n=3)
 sv.synchronize()
 out = []
