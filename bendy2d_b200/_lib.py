@@ -115,6 +115,7 @@ def signatures():
         "bendy_halo_stats": (i, [vp, u32p, u32p, u32p, u32p]),
         "bendy_plan_links": (i, [sz, u32p, sz, u32, u32, u32p, u32p, u32p, u32p, C.POINTER(ScheduleInfo)]),
         "bendy_plan_links_scheduled": (i, [sz, u32p, sz, u32, u32, i, u32p, u32p, u32p, u32p, C.POINTER(ScheduleInfo)]),
+        "bendy_debug_normalize": (i, [i, f32p, f32p, f32p, sz, f32p, f32p]),
     }
     return _SIGS
 

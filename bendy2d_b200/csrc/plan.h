@@ -18,7 +18,7 @@
 
 namespace bendy {
 
-struct LocalLink {  // 8 B record streamed by the partition kernel
+struct alignas(8) LocalLink {  // 8 B record streamed by the partition kernel (one 64-bit load)
     uint16_t a, b;  // partition-local point indices
     float len;
 };

@@ -2449,6 +2449,35 @@ int bendy_update_group(bendy_solver **group, int n, uint32_t n_updates, float dt
 }
 
 // ---- host-only planning ----------------------------------------------------------------------------
+int bendy_debug_normalize(int device, const float *dx, const float *dy, const float *norm, size_t n, float *nx, float *ny) {
+    if (n == 0) return BENDY_OK;
+    if (!dx || !dy || !norm || !nx || !ny || n > 0x7FFFFFF0u) {
+        g_last_error = "bendy_debug_normalize: null array or n too large";
+        return BENDY_ERR_ARG;
+    }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) {
+        g_last_error = "bendy_debug_normalize: no such device";
+        return BENDY_ERR_NO_DEVICE;
+    }
+    float *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 5 * n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d, dx, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + n, dy, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + 2 * n, norm, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_debug_normalize<<<((uint32_t)n + 255u) / 256u, 256>>>(d, d + n, d + 2 * n, (uint32_t)n, d + 3 * n, d + 4 * n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(nx, d + 3 * n, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ny, d + 4 * n, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (d) cudaFree(d);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("bendy_debug_normalize: ") + cudaGetErrorString(e);
+        return BENDY_ERR_CUDA;
+    }
+    return BENDY_OK;
+}
+
 int bendy_plan_links(size_t n_points, const uint32_t *ab, size_t n_links, uint32_t pack_points, uint32_t max_points,
                      uint32_t *rank, uint32_t *perm, uint32_t *link_colour, uint32_t *link_partition,
                      bendy_schedule_info *info) {

@@ -253,6 +253,13 @@ int bendy_plan_links_scheduled(size_t n_points, const uint32_t *ab, size_t n_lin
                                uint32_t max_points, int link_schedule, uint32_t *rank, uint32_t *perm,
                                uint32_t *link_colour, uint32_t *link_partition, bendy_schedule_info *info);
 
+/* Test hook, no solver needed: the normalize() of link.rs:24 / circle.rs:37 as the kernels compute it (both
+ * components over one refined reciprocal, kernels.cuh normalize2) for n host triples (dx, dy, norm) on `device`
+ * (-1 = current).  The parity tests compare it with IEEE binary32 division bit for bit over the operand ranges,
+ * the guard's edges, zeros of both signs, denormals, infinities and NaN. */
+int bendy_debug_normalize(int device, const float *dx, const float *dy, const float *norm, size_t n, float *nx,
+                          float *ny);
+
 #ifdef __cplusplus
 }
 #endif

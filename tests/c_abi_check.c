@@ -69,6 +69,10 @@ int main(void) {
     rc |= bendy_plan_links(2, ab, 1, 0, 0, rank, perm, NULL, NULL, &info);
     rc |= bendy_plan_links_scheduled(2, ab, 1, 0, 0, BENDY_LINKS_REFERENCE_ORDER, rank, perm, NULL, NULL, &info);
     {
+        float one = 1.f, two = 2.f, nxy[2];
+        rc |= bendy_debug_normalize(-1, &one, &one, &two, 1, &nxy[0], &nxy[1]);
+    }
+    {
         float last[7];
         int valid = 0;
         bendy_solver *c3;

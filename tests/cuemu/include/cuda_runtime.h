@@ -45,6 +45,9 @@ struct alignas(16) float4 {
 struct alignas(16) uint4 {
     uint32_t x, y, z, w;
 };
+struct alignas(8) uint2 {
+    uint32_t x, y;
+};
 struct uint3 {
     uint32_t x, y, z;
 };
@@ -54,6 +57,7 @@ struct dim3 {
 };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 
 using std::isfinite;
@@ -183,6 +187,12 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }  // one rounding (libm / FMA3)
+// stand-in for MUFU.RCP (rcp.approx): the correctly rounded reciprocal.  kernels.cuh normalize2 is ptxas' own div.rn
+// expansion with the reciprocal shared; like that expansion it is NOT independent of the seed (d = 0x1.fffffep+39,
+// a = 1: a seed one ulp low ends in a tie that rounds the wrong way), so what the emulation checks is the guard
+// logic around it; the quotient itself is checked on the device against IEEE division (tests/test_gpu_normalize.py)
+static inline float cuemu_rcp_seed(float d) { return 1.0f / d; }
 static inline long long __float2ll_rn(float a) { return llrintf(a); }  // round-to-nearest-even (default mode)
 static inline float __ll2float_rn(long long a) { return (float)a; }
 static inline uint32_t __float_as_uint(float a) { return cuemu::unpack<uint32_t>(cuemu::pack(a)); }
