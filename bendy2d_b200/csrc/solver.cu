@@ -745,8 +745,9 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
     bool same = s->prm_valid && std::memcmp(&p, &s->prm, sizeof p) == 0;
     if (same) return BENDY_OK;
     // grid shape changes invalidate captured launch dimensions
+    // (quad selects the narrowphase instance a captured graph holds)
     bool shape = !s->prm_valid || p.nx != s->prm.nx || p.ny != s->prm.ny || p.pnx != s->prm.pnx ||
-                 p.pny != s->prm.pny;
+                 p.pny != s->prm.pny || p.quad != s->prm.quad;
     if (shape) {
         drop_graph();
         if (discs) {
@@ -1132,8 +1133,16 @@ int Ops::launch_collide_integrate_discs(const SubstepCtx &c, int phase) {
              s->nP,    s->nOwned,   s->nC, s->d_crad.p,    s->d_circ_tile_count.p, s->d_circ_tile_ids.p, s->d_circ_acc.p,
              s->d_circ_snap.p, s->record_work ? s->d_chunk_work.p : nullptr, s->narrow_reverse ? 1u : 0u};
     const uint32_t blocks = cdiv(s->nOwned, NARROW_THREADS);
-#define NARROW(HK, HP) \
-    LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_contact_integrate<HK, HP>, blocks, NARROW_THREADS, 0, st, a, c.k4, c.prm))
+    const bool quad = s->prm.quad != 0;  // two candidate rows at most: the instance with the one-step index map
+#define NARROW(HK, HP)                                                                                                   \
+    do {                                                                                                                 \
+        if (quad)                                                                                                        \
+            LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_contact_integrate<HK, HP, true>, blocks,           \
+                                                 NARROW_THREADS, 0, st, a, c.k4, c.prm));                                \
+        else                                                                                                             \
+            LAUNCH(BENDY_K_NARROWPHASE, launch_k(c.pdl > 1, k2_narrow_contact_integrate<HK, HP, false>, blocks,          \
+                                                 NARROW_THREADS, 0, st, a, c.k4, c.prm));                                \
+    } while (0)
     if (c.K && c.contact)
         NARROW(true, true);
     else if (c.K)

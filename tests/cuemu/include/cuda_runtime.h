@@ -193,6 +193,12 @@ static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c);
 // a = 1: a seed one ulp low ends in a tie that rounds the wrong way), so what the emulation checks is the guard
 // logic around it; the quotient itself is checked on the device against IEEE division (tests/test_gpu_normalize.py)
 static inline float cuemu_rcp_seed(float d) { return 1.0f / d; }
+static inline int __float2int_rz(float a) {  // cvt.rzi.s32.f32: saturating, NaN -> 0
+    if (!(a == a)) return 0;
+    if (a >= 2147483648.0f) return 2147483647;
+    if (a <= -2147483648.0f) return -2147483647 - 1;
+    return (int)a;
+}
 static inline long long __float2ll_rn(float a) { return llrintf(a); }  // round-to-nearest-even (default mode)
 static inline float __ll2float_rn(long long a) { return (float)a; }
 static inline uint32_t __float_as_uint(float a) { return cuemu::unpack<uint32_t>(cuemu::pack(a)); }
