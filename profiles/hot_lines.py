@@ -25,9 +25,10 @@ for r in rows:
             ln = int(r[0])
         except ValueError:
             continue
-        inst = int(r[hdr["Instructions Executed"]] or 0)
-        tinst = int(r[hdr["Thread Instructions Executed"]] or 0)
-        samp = int(r[hdr["# Samples"]] or 0)
+        num = lambda v: int(v) if v not in ("", "-") else 0
+        inst = num(r[hdr["Instructions Executed"]])
+        tinst = num(r[hdr["Thread Instructions Executed"]])
+        samp = num(r[hdr["# Samples"]])
         e = lines.setdefault(ln, [r[1], 0, 0, 0])
         e[1] += inst
         e[2] += tinst
