@@ -718,6 +718,13 @@ int Ops::configure(float dt, float gx, float gy, float bx, float by, float bw, f
     p.hi_x = bx + bw;  // particle.rs:32
     p.hi_y = by + bh;  // particle.rs:41
     p.rp = s->particle_radius;
+    p.rs = p.rp + p.rp;  // circle.rs:36: r_a + r_b
+    p.rs2 = p.rs * p.rs;
+    p.rp2 = p.rp * p.rp;  // circle.rs:39-40
+    {
+        const volatile float two_rp2 = p.rp2 + p.rp2;  // (volatile: one rounding per operation, whatever the host flags)
+        p.scale_u = 1.0f / two_rp2;                    // circle.rs:41
+    }
     p.halo_xl = s->halo_on ? s->halo_xl : -INFINITY;
     p.halo_xr = s->halo_on ? s->halo_xr : INFINITY;
     p.stray_xl = s->halo_on ? s->stray_xl : -INFINITY;
