@@ -55,11 +55,16 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks/throttle reasons sampled under the benchmark's load (B200_PROFILING.md).  The timed region of
+    the default run lasts about ten milliseconds - less than one nvidia-smi sample - so the sampler is started before
+    the warm-up (nvidia-smi takes a moment to come up), the window that counts starts with the timed region and is
+    kept open over untimed steps of the same workload that follow it until it is ~0.5 s long (window_s, extra_steps in
+    the JSON); only samples whose own time stamp lies inside the window are used."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    WINDOW_S = 0.5
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
@@ -67,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -75,29 +80,39 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self) -> dict:
+    @staticmethod
+    def _stamp(text, fallback):
+        import datetime
+
+        try:
+            return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return fallback  # arrival time of the line
+
+    def stop(self, t_begin: float, t_end: float, extra_steps: int = 0) -> dict:
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.08)  # let the last line of the window arrive
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for arrived, r in list(self.rows):
             try:
-                sm.append(float(r[1]))
-                mx = float(r[2])
-                for n, v in zip(names, r[5:9]):
+                ts = self._stamp(r[0], arrived)
+                if not (t_begin <= ts <= t_end):
+                    continue
+                sm.append(float(r[2]))
+                mx = float(r[3])
+                for n, v in zip(names, r[6:10]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 continue
-        # under load = upper half of the samples (the sampler also sees the idle gaps between steps)
-        sm.sort()
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "window_s": round(t_end - t_begin, 3), "extra_steps": extra_steps,
+                "window": "the timed region + the untimed steps of the same workload that follow it"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -185,6 +200,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-clock-window", action="store_true",
+                    help="do not extend the nvidia-smi window with untimed steps (ncu launch lists)")
     ap.add_argument("--no-scaling-ref", action="store_true", help="skip the C5-on-one-GPU reference point")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (not the headline)")
     ap.add_argument("--no-parity-check", action="store_true", help="N>1: skip the sharded-vs-unsharded bit compare")
@@ -234,6 +251,9 @@ def main():
         sv.synchronize()
         return sv
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # before the warm-up: it has to be running when the timed region begins
     solver = fresh_solver()
     info = solver.schedule_info()
     log(f"[rank {rank}] scene {sc.name}: {sc.n_points} points, {sc.n_links} links, built in "
@@ -252,11 +272,9 @@ def main():
             torch.cuda.synchronize()
 
     # ---- timed region: K steps, each bracketed by events on the solver's stream
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = solver.launch_count()
     barrier()
+    clock_t0 = time.time()
     wall0 = time.perf_counter()
     total_ms = 0.0
     step_ms = []
@@ -272,7 +290,6 @@ def main():
     wall = time.perf_counter() - wall0
     if world > 1:
         solver.check_halo()  # overflow / stale ownership would make the run invalid: raise
-    clocks = sampler.stop() if rank == 0 else None
     gpu_launches = solver.launch_count() - launches0
     # ---- sharded runs: the final state of the timed run against the UNSHARDED 1-GPU run of the same updates
     # (C5 fits one GPU).  Puts the parity of the NCCL path into the bench record.
@@ -305,6 +322,27 @@ def main():
         gpu_launches = int(lt.item())
     ms_per_step = total_ms / args.steps
     value = n_points_total * sc.sub_steps * args.steps / (total_ms * 1e-3)
+    # ---- keep the clock window open under the same load (untimed; the step count is the same on every rank: it comes
+    # from the all-reduced step time; nothing below reads this solver's state again)
+    extra_steps = 0
+    left = ClockSampler.WINDOW_S - (time.time() - clock_t0)
+    if left > 0 and not args.no_clock_window:
+        budget = int(min(20000, max(1, left * 1e3 / max(ms_per_step, 1e-3))))
+        try:
+            if world > 1:  # the halo exchange is collective: the same count everywhere
+                solver.update(sc.dt, n=budget)
+                solver.synchronize()
+                extra_steps = budget
+            else:  # the scene gets slower as it piles up: in pieces, until the window is long enough
+                while extra_steps < budget and time.time() - clock_t0 < ClockSampler.WINDOW_S:
+                    n = min(32, budget - extra_steps)
+                    solver.update(sc.dt, n=n)
+                    solver.synchronize()
+                    extra_steps += n
+        except Exception as e:  # e.g. a strip that would need rebalancing by now: the window is as long as it got
+            log(f"[rank {rank}] clock window cut short: {e}")
+    barrier()
+    clocks = sampler.stop(clock_t0, time.time(), extra_steps) if rank == 0 else None
 
     # ---- warm-L2 figure (same steps back to back, one event pair) for context
     del solver

@@ -9,7 +9,7 @@ timeout 400 ncu --set full --clock-control none --import-source on -k "$K" -s 18
 timeout 600 ncu --set full --clock-control none --import-source on -k "$K" -s 1953 -c 9 -o gpurun_out/r2_final_c3_late \
     python profiles/ncu_c3_chain.py 27 1 > gpurun_out/r2_cap2.log 2>&1
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 180 --csv --log-file gpurun_out/r2_launches_bench_steps2.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-scaling-ref > gpurun_out/r2_cap3.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-scaling-ref --no-clock-window > gpurun_out/r2_cap3.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 1944 -c 72 --csv --log-file gpurun_out/r2_launches_c3_late.csv \
     python profiles/ncu_c3_chain.py 27 1 > gpurun_out/r2_cap4.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 200 -c 60 --csv --log-file gpurun_out/r2_launches_strip_rank.csv \

@@ -124,4 +124,7 @@ extern "C" {
     pub fn bendy_plan_links_scheduled(n_points: usize, ab: *const u32, n_links: usize, pack_points: u32, max_points: u32,
                                       link_schedule: c_int, rank: *mut u32, perm: *mut u32, link_colour: *mut u32,
                                       link_partition: *mut u32, info: *mut bendy_schedule_info) -> c_int;
+    // test hook: normalize() of link.rs:24 / circle.rs:37 as the kernels compute it, for n host triples
+    pub fn bendy_debug_normalize(device: c_int, dx: *const f32, dy: *const f32, norm: *const f32, n: usize,
+                                 nx: *mut f32, ny: *mut f32) -> c_int;
 }
