@@ -477,6 +477,19 @@ static cudaError_t upload(DevBuf<T> &d, const std::vector<T> &h, cudaStream_t st
 int Ops::rebuild() {
     if (int rc = bind()) return rc;
     if (int rc = pull()) return rc;
+    // The reference accepts any link when it is added and panics when it SOLVES one whose indices do not satisfy
+    // a < b < len (split_at_mut(b), split.0[a], split.1[0]: link.rs:19-21 / 37-39), i.e. inside the first update.
+    // Same place here: the scene is about to be planned for the device.
+    for (size_t k = 0; k < s->pl_len.size(); k++)
+        if (!(s->pl_ab[2 * k] < s->pl_ab[2 * k + 1]) || !(s->pl_ab[2 * k + 1] < s->p_pos.size()))
+            return fail(BENDY_ERR_LINK, "particle link " + std::to_string(k) + " (" + std::to_string(s->pl_ab[2 * k]) + ", " +
+                                            std::to_string(s->pl_ab[2 * k + 1]) + ") needs a < b < " +
+                                            std::to_string(s->p_pos.size()) + " particles: the reference panics here (link.rs:19-21)");
+    for (size_t k = 0; k < s->cl.size(); k++)
+        if (!(s->cl[k].a < s->cl[k].b) || !(s->cl[k].b < s->c_pos.size()))
+            return fail(BENDY_ERR_LINK, "circle link " + std::to_string(k) + " (" + std::to_string(s->cl[k].a) + ", " +
+                                            std::to_string(s->cl[k].b) + ") needs a < b < " + std::to_string(s->c_pos.size()) +
+                                            " circles: the reference panics here (link.rs:37-39)");
     drop_graph();
     s->nOwned = (uint32_t)s->p_pos.size();
     s->nP = s->nOwned + (s->halo_on ? 2 * s->ghost_cap : 0);  // disc slots = owned + ghosts
@@ -1686,7 +1699,8 @@ static bendy_solver *load_snapshot_impl(const char *path, int device) {
             why = "truncated snapshot";
         else if (fgetc(f) != EOF)
             why = "trailing bytes after the snapshot";
-        // the same index rules the add_* calls enforce (link.rs:19-21)
+        // a snapshot is the state of a scene that can be stepped: a link the reference could not solve (link.rs:19-21)
+        // makes the file invalid (the add_* calls accept such a link and the next update refuses it)
         for (uint64_t k = 0; !why && k < nPL; k++)
             if (!(t->pl_ab[2 * k] < t->pl_ab[2 * k + 1]) || !(t->pl_ab[2 * k + 1] < nP)) why = "particle link out of range";
         for (uint64_t k = 0; !why && k < nCL; k++)
@@ -1838,12 +1852,8 @@ int bendy_add_particle_links(bendy_solver *s, const uint32_t *ab, const float *l
     NEED(s);
     OPS;
     if (n && (!ab || !len)) return ops.fail(BENDY_ERR_ARG, "bendy_add_particle_links: null arrays");
-    const size_t np = s->p_pos.size();
-    for (size_t k = 0; k < n; k++)
-        if (!(ab[2 * k] < ab[2 * k + 1]) || !(ab[2 * k + 1] < np))
-            return ops.fail(BENDY_ERR_LINK,
-                            "bendy_add_particle_links: link needs a < b < particle count (the reference panics, "
-                            "link.rs:19-21)");
+    // like the reference, any pair is accepted here (solver.rs:62-64 pushes the link; a program may add its links
+    // before the particles they name): the indices are checked where link.rs:19-21 would panic, inside update
     if (int rc = edit_begin(s)) return rc;
     s->pl_ab.insert(s->pl_ab.end(), ab, ab + 2 * n);
     s->pl_len.insert(s->pl_len.end(), len, len + n);
@@ -1855,11 +1865,7 @@ int bendy_add_circle_links(bendy_solver *s, const uint32_t *ab, const float *len
     NEED(s);
     OPS;
     if (n && (!ab || !len)) return ops.fail(BENDY_ERR_ARG, "bendy_add_circle_links: null arrays");
-    const size_t nc = s->c_pos.size();
-    for (size_t k = 0; k < n; k++)
-        if (!(ab[2 * k] < ab[2 * k + 1]) || !(ab[2 * k + 1] < nc))
-            return ops.fail(BENDY_ERR_LINK, "bendy_add_circle_links: link needs a < b < circle count (the reference panics)");
-    if (int rc = edit_begin(s)) return rc;
+    if (int rc = edit_begin(s)) return rc;  // indices are checked inside update, like the reference (link.rs:37-39)
     for (size_t k = 0; k < n; k++) s->cl.push_back(GlobalLink{ab[2 * k], ab[2 * k + 1], len[k]});
     edit_end(s);
     return BENDY_OK;

@@ -72,10 +72,11 @@ int bendy_add_circles(bendy_solver *s, const float *pos_xy, const float *prev_xy
  * (polygon.rs:8-14). */
 int bendy_add_polygon(bendy_solver *s, const float *pos_xy, const float *prev_xy, const float *acc_xy, size_t nv,
                       const uint32_t *link_ab, const float *link_len, size_t nl, int is_static, float cx, float cy);
-/* Solver::add_particle_link (solver.rs:62-64) x n; ab = (a0,b0,a1,b1,...).  Validates a<b<len at
- * add time and returns BENDY_ERR_LINK where the reference would panic inside update. */
+/* Solver::add_particle_link (solver.rs:62-64) x n; ab = (a0,b0,a1,b1,...).  Like the reference, any pair is accepted
+ * here (links may be added before the particles they name); a link that does not satisfy a < b < len when the scene
+ * is stepped makes bendy_update return BENDY_ERR_LINK where the reference panics (link.rs:19-21). */
 int bendy_add_particle_links(bendy_solver *s, const uint32_t *ab, const float *len, size_t n);
-/* Solver::add_circle_link (solver.rs:65-67) x n */
+/* Solver::add_circle_link (solver.rs:65-67) x n; indices are checked inside update as well (link.rs:37-39) */
 int bendy_add_circle_links(bendy_solver *s, const uint32_t *ab, const float *len, size_t n);
 
 /* ---------------------------------------------------------------- the hot path */

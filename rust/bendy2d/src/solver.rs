@@ -10,7 +10,8 @@
 //! `Debug` (solver.rs:19) is implemented by hand over the synchronised mirrors.
 //!
 //! Differences a caller can observe:
-//!  * an invalid link panics at `add_*_link` (the reference panics inside `update`, link.rs:19-21);
+//!  * an invalid particle / circle link panics inside `update`, like the reference (link.rs:19-21); only a polygon's
+//!    own links are checked when the polygon is added;
 //!  * the host-side helpers the reference's own `update` is made of (`Particle::update`, `solve_bounds`,
 //!    `Circle::solve_circle`, `ParticleLink::solve`, `Polygon::solve_*` ...) are not re-exported: that arithmetic
 //!    runs on the device, and a host call on a mirror would be overwritten by the next refresh;

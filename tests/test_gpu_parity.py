@@ -112,14 +112,43 @@ def test_kat_circle_pair_and_bounds_inset():
 
 
 def test_link_validation_matches_reference_panic():
-    g = Solver()
-    g.add_particles([[0, 0], [1, 0]])
+    """solver.rs:62-67 pushes any link; link.rs:19-21 / 37-39 panic when a link with a >= b or b >= len is SOLVED,
+    i.e. inside update.  Same here: add accepts, update raises (and keeps raising: the scene cannot be stepped)."""
     for a, b in ((1, 1), (1, 0), (0, 2)):
+        g = Solver()
+        g.add_particles([[0, 0], [1, 0]])
+        g.add_particle_link(ParticleLink(Link(a, b, 1.0)))
+        for _ in range(2):
+            with pytest.raises(LinkPanic):
+                g.update(0.01)
+        p, _ = g.read_particles()  # the host scene is intact
+        assert p.tolist() == [[0.0, 0.0], [1.0, 0.0]]
+        g = Solver()
+        g.add_circle(Circle(Particle([0.0, 0.0]), 1.0))
+        g.add_circle(Circle(Particle([5.0, 0.0]), 1.0))
+        g.add_circle_link(CircleLink(Link(a, b, 4.0)))
         with pytest.raises(LinkPanic):
-            g.add_particle_link(ParticleLink(Link(a, b, 1.0)))
-    g.add_particle_link(ParticleLink(Link(0, 1, 1.0)))
-    g.update(0.01)
-    g.synchronize()
+            g.update(0.01)
+
+
+def test_links_may_be_added_before_their_particles():
+    """legal for the reference (nothing is indexed before update): same bits as the usual order"""
+    pts = [[10.0, 10.0], [11.0, 10.0], [11.0, 11.5]]
+    links = [(0, 1, 0.8), (1, 2, 1.2), (0, 2, 2.0)]
+    a, b = Solver(), Solver()
+    for s in (a, b):
+        s.gravity = (0.0, 98.2)
+    for i, j, l in links:
+        a.add_particle_link(ParticleLink(Link(i, j, l)))
+    a.add_particles(pts)
+    b.add_particles(pts)
+    for i, j, l in links:
+        b.add_particle_link(ParticleLink(Link(i, j, l)))
+    for _ in range(5):
+        a.update(0.01)
+        b.update(0.01)
+    for x, y in zip(a.read_particles(), b.read_particles()):
+        assert np.array_equal(bits(x), bits(y))
 
 
 def test_empty_solver_and_getters():
