@@ -112,7 +112,8 @@ class ClockSampler:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm), "window_s": round(t_end - t_begin, 3), "extra_steps": extra_steps,
-                "window": "the timed region + the untimed steps of the same workload that follow it"}
+                "window": "the timed region + what follows it on this GPU: untimed steps of the same workload (one GPU) / "
+                          "the sharded-vs-unsharded parity check (several)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -322,24 +323,21 @@ def main():
         gpu_launches = int(lt.item())
     ms_per_step = total_ms / args.steps
     value = n_points_total * sc.sub_steps * args.steps / (total_ms * 1e-3)
-    # ---- keep the clock window open under the same load (untimed; the step count is the same on every rank: it comes
-    # from the all-reduced step time; nothing below reads this solver's state again)
+    # ---- keep the clock window open under the same load (untimed; nothing below reads this solver's state again).
+    # One GPU: further steps of the same workload, in pieces (the scene gets slower as it piles up), until the window
+    # is long enough.  Several GPUs: no extra steps (every substep is a collective: ranks that disagreed on a count,
+    # or one rank raising, would hang the others); there the window ends after the sharded-vs-unsharded parity check,
+    # which steps the same scene on GPU 0.
     extra_steps = 0
-    left = ClockSampler.WINDOW_S - (time.time() - clock_t0)
-    if left > 0 and not args.no_clock_window:
-        budget = int(min(20000, max(1, left * 1e3 / max(ms_per_step, 1e-3))))
+    if world == 1 and not args.no_clock_window:
+        budget = int(min(20000, ClockSampler.WINDOW_S * 1e3 / max(ms_per_step, 1e-3)))
         try:
-            if world > 1:  # the halo exchange is collective: the same count everywhere
-                solver.update(sc.dt, n=budget)
+            while extra_steps < budget and time.time() - clock_t0 < ClockSampler.WINDOW_S:
+                n = min(32, budget - extra_steps)
+                solver.update(sc.dt, n=n)
                 solver.synchronize()
-                extra_steps = budget
-            else:  # the scene gets slower as it piles up: in pieces, until the window is long enough
-                while extra_steps < budget and time.time() - clock_t0 < ClockSampler.WINDOW_S:
-                    n = min(32, budget - extra_steps)
-                    solver.update(sc.dt, n=n)
-                    solver.synchronize()
-                    extra_steps += n
-        except Exception as e:  # e.g. a strip that would need rebalancing by now: the window is as long as it got
+                extra_steps += n
+        except Exception as e:  # the window is as long as it got
             log(f"[rank {rank}] clock window cut short: {e}")
     barrier()
     clocks = sampler.stop(clock_t0, time.time(), extra_steps) if rank == 0 else None
