@@ -116,6 +116,37 @@ class ClockSampler:
                           "the sharded-vs-unsharded parity check (several)"}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """One process per GPU: keep this rank's threads - and with them the first-touch placement of its pinned staging
+    buffers - on the NUMA node its GPU hangs off, so that the e2e leg's host<->device copies do not cross the socket
+    interconnect.  Best effort: any surprise (no sysfs, node -1, an empty intersection with the allowed CPUs) leaves
+    the affinity alone.  Returns a short note for the log."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(index)  # the CUDA device itself (CUDA_VISIBLE_DEVICES may renumber)
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0].strip().lower()
+            bdf = out[-12:] if len(out) >= 12 else out  # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return f"GPU {index} ({bdf}): no NUMA node reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"GPU {index} ({bdf}): node {node} has none of the allowed CPUs"
+        os.sched_setaffinity(0, cpus)
+        return f"GPU {index} ({bdf}): bound to NUMA node {node} ({len(cpus)} CPUs)"
+    except Exception as e:
+        return f"GPU {index}: NUMA binding skipped ({type(e).__name__}: {e})"
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_baseline_sample(workload: str):
     """Bounded sample of the workload for the CPU oracle (BASELINE.md "CPU-baseline plan"): the scene at FULL SIZE
@@ -201,6 +232,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: leave the CPU affinity of the ranks alone")
     ap.add_argument("--no-clock-window", action="store_true",
                     help="do not extend the nvidia-smi window with untimed steps (ncu launch lists)")
     ap.add_argument("--no-scaling-ref", action="store_true", help="skip the C5-on-one-GPU reference point")
@@ -223,6 +255,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: bendy2d_b200 has no CPU path")
     torch.cuda.set_device(local)
+    numa_note = bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa_bind else "not bound (single process)"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -257,6 +290,7 @@ def main():
         sampler.start()  # before the warm-up: it has to be running when the timed region begins
     solver = fresh_solver()
     info = solver.schedule_info()
+    log(f"[rank {rank}] {numa_note}")
     log(f"[rank {rank}] scene {sc.name}: {sc.n_points} points, {sc.n_links} links, built in "
         f"{time.perf_counter() - t_build:.1f}s; schedule {info}")
 
