@@ -64,3 +64,31 @@ def test_committed_bench_line_follows_the_contract():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] == 1 and c["value"] > 0 and "sample" in c
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_committed_round2_bench_lines_are_consistent():
+    """profiles/r2_bench_c{1..4}_n1.json (final build of round 2, B200): contract keys, value = points x substeps / time,
+    roofline fractions recomputable from their own fields, clocks sampled under load with no thermal / hw slowdown."""
+    for w in ("c1", "c2", "c3", "c4"):
+        with open(os.path.join(ROOT, "profiles", f"r2_bench_{w}_n1.json")) as f:
+            d = json.loads(f.read().strip().splitlines()[-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+            assert key in d, (w, key)
+        sub = d["config"]["substeps_per_step"]
+        assert abs(d["value"] - d["config"]["points"] * sub / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6, w
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9, w
+        whole = r["substep"]
+        assert abs(whole["achieved"] - whole["alg_bytes"] * sub / (d["ms_per_step"] * 1e-3) / 1e9) / whole["achieved"] < 1e-6, w
+        assert abs(whole["frac"] - whole["achieved"] / r["peak"]) < 1e-9, w
+        assert d["gpu_launches"] > 0 and d["vs_baseline"] is None and d["dtype"] == "f32"
+        c = d["clocks"]
+        assert c["samples"] >= 3 and c["sm_mhz"] == c["sm_max_mhz"], (w, c)
+        assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert 0 < d["e2e"]["value"] < d["value"] and d["e2e"]["h2d_bytes_per_step"] > 0
+    # the headline: C3 on one GPU, contract bytes 228.4 MB per substep
+    with open(os.path.join(ROOT, "profiles", "r2_bench_c3_n1.json")) as f:
+        c3 = json.loads(f.read().strip().splitlines()[-1])
+    assert c3["roofline"]["substep"]["alg_bytes"] == 228402400 and c3["value"] > 1.75e10
+    assert c3["roofline"]["traffic"] is not None and c3["roofline"]["traffic"] < c3["roofline"]["alg_bytes_per_substep_kernel"]
